@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the retrieval hot path (BASELINE.json: queries/sec at 10M subsessions,
+d=128, top-100; fused per-session subsession-max + top-k; configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+A "step" answers one batch of nq=1000 query sessions against the whole database and returns the top-100
+sessions per query.  With N>1 ranks the database rows are sharded row-wise at session boundaries (strong
+scaling: the 10M-row database is fixed), every rank searches its shard, and the per-rank (score, id)
+candidates are merged after ONE NCCL all-gather.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec at 10M subsessions d=128 top-100"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--nq", type=int, default=1000)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--mode", default="exact", choices=["exact", "bf16", "fp32"])
+    ap.add_argument("--reduce", default="max", choices=["max", "sum", "none"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    return ap.parse_args()
+
+
+def session_lengths(total_rows, seed):
+    """1 + Poisson(7) subsession rows per session until total_rows are used"""
+    rng = np.random.default_rng(seed)
+    lens = []
+    left = total_rows
+    while left > 0:
+        blk = 1 + rng.poisson(7, size=max(1024, left // 8 + 1))
+        c = np.cumsum(blk)
+        cut = int(np.searchsorted(c, left, side="left"))
+        if cut < len(blk):
+            blk = blk[:cut + 1].copy()
+            blk[-1] -= int(c[cut] - left)
+            lens.append(blk[blk > 0])
+            left = 0
+        else:
+            lens.append(blk)
+            left -= int(c[-1])
+    lens = np.concatenate(lens).astype(np.int64)
+    assert lens.sum() == total_rows
+    return lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def host_sample(rows, d, seed):
+    """host copy of the workload generator for the CPU arm (same distribution, numpy RNG)"""
+    lens = session_lengths(rows, seed)
+    rng = np.random.default_rng(seed + 1)
+    base = rng.standard_normal((len(lens), d), dtype=np.float32)
+    db = np.repeat(base, lens, axis=0)
+    db += 0.3 * rng.standard_normal(db.shape, dtype=np.float32)
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    return db, seg, base
+
+
+def run_reference(a):
+    """The reference's CPU path for this workload (faiss IndexFlatIP over normalize(emb),
+    test_amazon_filterd.py:207-214,578, restated by oracle.search_blas since faiss is not installable):
+    all host threads, a bounded row sample per step, extrapolated linearly in rows."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import search_oracle as so
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = min(a.cpu_sample_rows, a.rows)
+    db, seg, base = host_sample(sample, a.d, 1234)
+    dbn = so.normalize_util_numpy(db)
+    rng = np.random.default_rng(99)
+    q = base[rng.integers(0, len(base), size=a.nq)] + 0.3 * rng.standard_normal((a.nq, a.d), dtype=np.float32)
+    red = {"max": so.REDUCE_MAX, "sum": so.REDUCE_SUM, "none": so.REDUCE_NONE}[a.reduce]
+    for _ in range(a.warmup):
+        so.search_blas(dbn, so.normalize_util_numpy(q), a.k, seg_off=seg, reduce=red, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        so.search_blas(dbn, so.normalize_util_numpy(q), a.k, seg_off=seg, reduce=red, threads=cores)
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    scale = a.rows / float(sample)
+    value = a.nq / (dt * scale)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d rows per step (%.3f s/step measured), time scaled linearly in rows"
+                                   % (sample, a.rows, dt)},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(a):
+    return {"workload": "configs[2]: %d subsession rows (sessions of 1+Poisson(7) contiguous rows), d=%d, nq=%d, "
+                        "fused per-session %s + top-%d, cosine" % (a.rows, a.d, a.nq, a.reduce, a.k),
+            "rows": a.rows, "d": a.d, "nq": a.nq, "k": a.k, "reduce": a.reduce, "mode": a.mode,
+            "sharding": "rows/%d at session boundaries + 1 NCCL all-gather merge" % a.gpus if a.gpus > 1 else "none",
+            "l2": "inputs larger than L2 (database %.2f GB bf16 per pass)" % (a.rows * a.d * 2 / 1e9)}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    import sessionsimilaritysearch_b200 as sss
+    from sessionsimilaritysearch_b200.dist import ShardedIndex
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic database, generated on the device shard by shard -------------------------------
+    lens_all = session_lengths(a.rows, 1234)
+    n_sess_all = len(lens_all)
+    s_lo = n_sess_all * rank // world
+    s_hi = n_sess_all * (rank + 1) // world
+    lens = lens_all[s_lo:s_hi]
+    row_off = int(lens_all[:s_lo].sum())
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321 + rank)
+    inner = sss.IndexFlatIP(a.d, device=local_rank, id_offset=(s_lo if a.reduce != "none" else row_off), mode=a.mode)
+    lens_t = torch.from_numpy(lens).to(dev)
+    host_rows = []
+    chunk = 131072
+    base_for_q = None
+    for c0 in range(0, len(lens), chunk):
+        l = lens_t[c0:c0 + chunk]
+        base = torch.randn((l.numel(), a.d), generator=g, device=dev)
+        if base_for_q is None:
+            base_for_q = base[:8192].clone()
+        rows = torch.repeat_interleave(base, l, dim=0)
+        rows += 0.3 * torch.randn(rows.shape, generator=g, device=dev)
+        inner.add(rows, norm=sss.NORM_UTIL)
+        if rank == 0 and not a.no_cpu_baseline and sum(x.shape[0] for x in host_rows) < a.cpu_sample_rows:
+            host_rows.append(rows.cpu().numpy())
+        del rows, base
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    if a.reduce != "none":
+        inner.set_segments(seg, a.reduce)
+    index = ShardedIndex(inner, world_size=world, rank=rank) if world > 1 else inner
+
+    # ---- queries: noisy copies of database sessions (a query subsession resembles its session) ------
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(99)  # same queries on every rank
+    if world > 1:
+        dist.broadcast(base_for_q, src=0)
+    pick = torch.randint(0, base_for_q.shape[0], (a.nq,), generator=gq, device=dev)
+    q_dev = sss.normalize(base_for_q[pick] + 0.3 * torch.randn((a.nq, a.d), generator=gq, device=dev))
+    q_host = torch.empty((a.nq, a.d), dtype=torch.float32).pin_memory()
+    q_host.copy_(q_dev)
+    q_np = q_host.numpy()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev():
+        return index.search(q_dev, a.k)
+
+    def step_e2e():
+        return index.search(q_np, a.k)
+
+    for _ in range(a.warmup):
+        step_dev()
+    inner.set_profiling(True)
+    scan_ns = [0, 0]
+
+    def step_dev_prof():
+        r = step_dev()
+        st = inner.stats()
+        scan_ns[0] += st["scan_ns"]
+        scan_ns[1] += st["scan_launches"]
+        return r
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_dev_prof, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    inner.set_profiling(False)
+    kernels_per_step = inner.stats()["kernels"] + (1 if world > 1 else 0)
+    waves = inner.stats()["waves"]
+    reruns = inner.stats()["reruns"]
+    for _ in range(max(1, a.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    ms_step = ms_total / a.steps
+    value = a.nq / (ms_step * 1e-3)
+    e2e_value = a.nq / (ms_e2e / a.steps * 1e-3)
+
+    extra = {}
+    if not a.no_extra and world == 1:
+        for mode, steps in (("bf16", 5), ("fp32", 2)):
+            if mode == a.mode:
+                continue
+            try:
+                fn = lambda: inner.search(q_dev, a.k, mode=mode)
+                fn()
+                extra[mode + "_qps"] = a.nq / (timed(fn, steps) / steps * 1e-3)
+            except RuntimeError as e:
+                extra[mode + "_qps"] = "error: %s" % e
+        # agreement of the headline mode with the bit-faithful fp32 mode on this very workload
+        try:
+            D1, I1 = inner.search(q_dev, a.k)
+            D2, I2 = inner.search(q_dev, a.k, mode="fp32")
+            extra["ids_equal_fp32_mode"] = bool(torch.equal(I1, I2))
+            extra["scores_equal_fp32_mode"] = bool(torch.equal(D1, D2))
+        except RuntimeError as e:
+            extra["ids_equal_fp32_mode"] = "error: %s" % e
+        # DB-stream-bound regime: one query per pass
+        try:
+            fn = lambda: inner.search(q_dev[:1], a.k)
+            fn()
+            ms1 = timed(fn, 10) / 10
+            extra["nq1_ms"] = ms1
+            extra["nq1_db_stream_gbs"] = a.rows * a.d * 2 / (ms1 * 1e-3) / 1e9
+        except RuntimeError as e:
+            extra["nq1_ms"] = "error: %s" % e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    rows_local = int(seg[-1])
+    flops_per_step = 2.0 * a.nq * rows_local * a.d
+    scan_s = scan_ns[0] * 1e-9 / a.steps
+    tensor_mode = a.mode in ("exact", "bf16")
+    if tensor_mode:
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        achieved = flops_per_step / scan_s / 1e12 if scan_s > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind + " sustained bf16",
+                    "kernel": "scan_bf16_kernel", "launches_per_step": scan_ns[1] / a.steps,
+                    "kernel_ms_per_step": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / ms_step,
+                    "algorithmic": "2*nq*rows*d flop = %.3e per step" % flops_per_step}
+    else:
+        peak = 2 * 148 * 128 * 1.965e9 / 1e12  # fp32 FMA peak of the CUDA cores (nominal clocks)
+        achieved = flops_per_step / scan_s / 1e12 if scan_s > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_kind": "nominal fp32 CUDA-core FMA peak (no tensor path in fp32 mode)",
+                    "kernel": "scan_fp32_kernel"}
+    tfile = os.path.join(ROOT, "profiles", "scan_traffic_bytes_per_step.json")
+    if os.path.exists(tfile):
+        try:
+            roofline["traffic"] = json.load(open(tfile)).get("bytes_per_step")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline and world == 1:
+        from oracle import search_oracle as so
+        cores = os.cpu_count() or 1
+        hdb = np.concatenate(host_rows, axis=0)
+        n_s = int(np.searchsorted(seg, min(a.cpu_sample_rows, hdb.shape[0]), side="right") - 1)
+        n_rows_s = int(seg[n_s])
+        hdb = so.normalize_util_numpy(hdb[:n_rows_s])
+        red = {"max": so.REDUCE_MAX, "sum": so.REDUCE_SUM, "none": so.REDUCE_NONE}[a.reduce]
+        so.search_blas(hdb[:65536], q_np, a.k, threads=cores)  # thread-pool warm-up
+        t0 = time.perf_counter()
+        Dc, Ic = so.search_blas(hdb, q_np, a.k, seg_off=seg[:n_s + 1], reduce=red, threads=cores)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": a.nq / (dt * a.rows / n_rows_s), "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": "first %d of %d rows (%d sessions), %.2f s measured, time scaled linearly in rows"
+                                  % (n_rows_s, a.rows, n_s, dt)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
+        "config": workload_config(a),
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(a.nq * a.d * 4),
+                "d2h_bytes_per_step": int(a.nq * a.k * 12), "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(kernels_per_step * a.steps),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "waves_per_step": waves, "overflow_reruns": reruns,
+        "extra": extra,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * sss_b200.h — C ABI of libsss_b200.so, the B200-native (sm_100a) retrieval hot path of
+ * SessionSimilaritySearch.
+ *
+ * The reference has no FFI: its "interface" for this path is a handful of Python calls into faiss
+ * and PyG (all file:line citations are into the reference tree):
+ *
+ *   build_index(emb, metric)          test_amazon_filterd.py:207-223   -> sss_index_create + sss_index_add
+ *   index.add(x)                      test_amazon_filterd.py:214,217,220; fine_tune_ours.py:843,849
+ *   index.search(x, K) -> (D, I)      test_amazon_filterd.py:578; fine_tune_ours.py:876,882 -> sss_index_search
+ *   normalize(vec)                    util_amazon_filtered.py:28-31; fine_tune_ours.py:38-40 -> sss_normalize
+ *   faiss.IndexBinaryFlat             fine_tune_ours.py:839-843,871-876 -> sss_binary_*
+ *   get_prediction_by_knn             test_amazon_filterd.py:59-78     -> sss_item_vote
+ *   encoder(data) (GNN + pooling)     model/model.py:279-351, model/gnn.py:64-81,193-217 -> sss_encoder_*
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on failure; sss_last_error() then returns a
+ *     message for the calling thread (the Python facade re-raises it as RuntimeError, mirroring the
+ *     reference's `raise RuntimeError(...)` convention, test_amazon_filterd.py:222).
+ *   - plain pointers and sizes only.  `*_on_device` says whether a buffer is a CUDA device pointer
+ *     (on the handle's device) or host memory; the library owns only its handle and workspaces.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream).  Host-buffer calls synchronise that stream before returning (their results are
+ *     on the host); device-buffer search calls synchronise it only to read back an 8-byte status word
+ *     (candidate-list overflow -> automatic rerun with a safe schedule; kernel watchdog).
+ *   - handles are not thread-safe; one handle per GPU for row-sharded search.
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SSS_B200_H
+#define SSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sss_index sss_index_t;
+typedef struct sss_binary_index sss_binary_index_t;
+typedef struct sss_encoder sss_encoder_t;
+
+/* metric of a flat index (faiss.IndexFlatIP / IndexFlatL2, test_amazon_filterd.py:211-220) */
+enum { SSS_METRIC_IP = 0, SSS_METRIC_L2 = 1 };
+
+/* row normalisation applied by sss_index_add / sss_normalize */
+enum {
+  SSS_NORM_NONE = 0,
+  SSS_NORM_UTIL = 1,  /* v / sqrt(clip(sum v^2, 1e-6))   util_amazon_filtered.py:28-31 */
+  SSS_NORM_FT = 2,    /* v / (||v||_2 + 1e-4)            fine_tune_ours.py:38-40 */
+  SSS_NORM_TORCH = 3  /* v / max(||v||_2, 1e-12)         F.normalize, fine_tune_ours.py:133,480,494 */
+};
+
+/* search mode */
+enum {
+  SSS_MODE_EXACT = 0, /* tcgen05 bf16 filter + fixed-order fp32 rescoring: ids and scores bit-identical to FP32 */
+  SSS_MODE_FP32 = 1,  /* CUDA-core fixed-order fp32 FMA scan (k-ascending), the bit-faithful restatement */
+  SSS_MODE_BF16 = 2   /* tcgen05 bf16 x bf16 -> fp32 scores returned as computed by the tensor core */
+};
+
+/* per-session reduction of subsession (row) scores; segments are contiguous row ranges */
+enum { SSS_REDUCE_NONE = 0, SSS_REDUCE_MAX = 1, SSS_REDUCE_SUM = 2 };
+
+const char* sss_last_error(void);
+/* library/ABI version, and the compute capability the kernels were built for (100 = sm_100a) */
+int sss_version(void);
+int sss_built_for_sm(void);
+
+/* ---- flat index (replaces faiss.IndexFlatIP / IndexFlatL2) --------------------------------------- */
+
+/* d: embedding width (any d >= 1).  id_offset: added to every returned id (row shard base). */
+int sss_index_create(sss_index_t** out, int device, int d, int metric, int64_t id_offset);
+int sss_index_destroy(sss_index_t* ix);
+
+/* Append n rows of fp32 [n, d] (row-major).  norm_mode is applied on the GPU before storing.
+ * Replaces index.add(normalize(emb)) / index.add(emb). */
+int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int rows_on_device, int norm_mode,
+                  void* stream);
+
+/* Declare contiguous segments (sessions): seg_off[n_seg+1] (host, int64), seg_off[0]==0,
+ * seg_off[n_seg]==ntotal.  reduce = MAX: score(session) = max over its rows; SUM: sum over its rows
+ * (computed as <q, sum of rows>, rows summed in row order).  Returned ids are then session indices. */
+int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce);
+
+int64_t sss_index_ntotal(const sss_index_t* ix);
+int sss_index_dim(const sss_index_t* ix);
+
+/* Top-k search.  q: fp32 [nq, d].  D: fp32 [nq, k] best first (IP: descending inner product;
+ * L2: ascending squared distance).  I: int64 [nq, k].  Ties: smaller id first.  If fewer than k
+ * results exist the tail is (IP: -inf, L2: +inf, id -1).  Replaces index.search(x, K). */
+int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
+                     float* D, int64_t* I, int out_on_device, void* stream);
+
+/* Counters of the last search on this handle.  what: 0 = kernels launched, 1 = scan waves,
+ * 2 = overflow reruns, 3 = scan-kernel device time in ns, 4 = scan-kernel launches (3 and 4 need
+ * sss_index_set_profiling(ix, 1): CUDA events are then recorded around every scan launch on the caller's
+ * stream). */
+int64_t sss_index_stat(const sss_index_t* ix, int what);
+int sss_index_set_profiling(sss_index_t* ix, int on);
+
+/* Row L2 normalisation of fp32 [n, d] into out (may alias in).  Replaces normalize(). */
+int sss_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, int on_device, int device,
+                  void* stream);
+
+/* k-way merge of per-shard candidates after the all-gather: cand_D fp32 [n_shards, nq, k],
+ * cand_I int64 [n_shards, nq, k] (device) -> D [nq, k], I [nq, k] (device).  Same order rule as
+ * sss_index_search; ids < 0 are padding. */
+int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_shards, int64_t nq, int k, int metric,
+                   float* D, int64_t* I, int device, void* stream);
+
+/* ---- binary index (replaces faiss.IndexBinaryFlat, fine_tune_ours.py:839-843,871-876) ------------ */
+
+/* nbits must be a multiple of 8; codes are uint8 [n, nbits/8] as produced by np.packbits(axis=1). */
+int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset);
+int sss_binary_destroy(sss_binary_index_t* ix);
+int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream);
+int64_t sss_binary_ntotal(const sss_binary_index_t* ix);
+/* D: int32 [nq, k] Hamming distances ascending, I: int64 [nq, k]; ties: smaller id first. */
+int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64_t nq, int k, int q_on_device,
+                      int32_t* D, int64_t* I, int out_on_device, void* stream);
+
+/* sign-binarise + pack: x fp32 [n, nbits_in] -> codes uint8 [n, ceil(nbits_in/8)], bit = (x > 0),
+ * MSB first, zero padded: the (d+1)/2 -> astype(int) -> np.packbits of fine_tune_ours.py:839-840 applied
+ * to BinarizeHead's {-1,0,+1} output (model/model.py:137). */
+int sss_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits_in, int on_device, int device,
+                       void* stream);
+
+/* ---- item vote (replaces get_prediction_by_knn, test_amazon_filterd.py:59-78) -------------------- */
+
+/* For each of nq queries: neighbours I[q, 0..s) with weights D[q, 0..s); every item of neighbour
+ * session j (items[item_off[j] .. item_off[j+1])) receives weight D[q, j]; weights are summed per item
+ * in neighbour order; the top-K items by (weight desc, item id asc) are written to out_items [nq, K]
+ * (-1 padded) and out_w [nq, K].  All buffers on the device. */
+int sss_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int64_t* item_off,
+                  const int64_t* items, int64_t n_sessions, int K, int64_t* out_items, float* out_w, int device,
+                  void* stream);
+
+/* ---- session encoder (replaces UnifyPoolingGraphLevelEncoder.forward after the text embedder) ----- */
+
+/* Shapes of the reference model (pretrain_filtered_amazon.py:262-287): in_dim 768, hidden 800,
+ * layers 3, out 1600, max_seq_len 20.  Weights are fp32, row-major [out, in] as in torch state_dicts. */
+typedef struct sss_encoder_shape {
+  int in_dim;      /* 768 */
+  int hidden;      /* 800 */
+  int n_layers;    /* 3 */
+  int out_dim;     /* 1600 */
+  int max_seq_len; /* 20 */
+} sss_encoder_shape_t;
+
+int sss_encoder_create(sss_encoder_t** out, int device, const sss_encoder_shape_t* shape);
+int sss_encoder_destroy(sss_encoder_t* enc);
+/* Upload one named parameter (names follow the reference state_dict), fp32, host or device. */
+int sss_encoder_set_param(sss_encoder_t* enc, const char* name, const float* data, int64_t numel, int on_device,
+                          void* stream);
+
+/* One batch of session graphs in CSR-free COO form, exactly the attributes the reference reads from a
+ * PyG HeteroDataBatch (model/model.py:283-286,317; model/gnn.py:199-206).  All pointers are device. */
+typedef struct sss_graph_batch {
+  int64_t n_graphs;
+  int64_t n_query;         /* query nodes */
+  int64_t n_product;       /* distinct product nodes */
+  int64_t n_expanded;      /* sum(cnt) product occurrences */
+  const float* x_query;    /* [n_query, in_dim] text features */
+  const float* x_product;  /* [n_product, in_dim] */
+  const int64_t* query_batch;    /* [n_query] graph id */
+  const int64_t* product_batch;  /* [n_product] */
+  const int64_t* query_pos;      /* [n_query] pos_emb_id */
+  const int64_t* product_cnt;    /* [n_product] */
+  const int64_t* product_pos;    /* [n_expanded] pos_emb_id grouped by product */
+  int64_t e_qp; const int64_t* qp_src; const int64_t* qp_dst; /* ('query','clicks','product') */
+  int64_t e_pq; const int64_t* pq_src; const int64_t* pq_dst; /* ('product','clicked by','query') */
+  int64_t e_pp; const int64_t* pp_src; const int64_t* pp_dst; /* ('product','to','product') */
+} sss_graph_batch_t;
+
+/* out: fp32 [n_graphs, out_dim] (device).  nonfinite (device int32, may be NULL) is set to 1 if any
+ * input feature is NaN (the reference's isnan asserts, model/model.py:301-314, without host syncs). */
+int sss_encoder_forward(sss_encoder_t* enc, const sss_graph_batch_t* batch, float* out, int32_t* nonfinite,
+                        void* stream);
+
+/* BinarizeHead eval forward, mlp=None (model/model.py:117-138): out = sign(x W^T + b) in {-1,0,+1}.
+ * x [n, in], W [out, in], b [out], out [n, out]; device pointers. */
+int sss_binarize_head(const float* x, const float* W, const float* b, int64_t n, int in_dim, int out_dim,
+                      float* out, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSS_B200_H */

@@ -1,0 +1,11 @@
+"""sessionsimilaritysearch_b200 — B200-native (sm_100a) retrieval hot path of SessionSimilaritySearch.
+
+Host side mirrors the reference's Python call surface; all arithmetic runs in libsss_b200.so.
+"""
+from ._lib import (METRIC_IP, METRIC_L2, MODE_BF16, MODE_EXACT, MODE_FP32, NORM_FT, NORM_NONE, NORM_TORCH, NORM_UTIL,
+                   REDUCE_MAX, REDUCE_NONE, REDUCE_SUM)
+from .index import IndexBinaryFlat, IndexFlatIP, IndexFlatL2, build_index, normalize, pack_sign_bits
+
+__all__ = ["IndexFlatIP", "IndexFlatL2", "IndexBinaryFlat", "build_index", "normalize", "pack_sign_bits",
+           "METRIC_IP", "METRIC_L2", "MODE_EXACT", "MODE_FP32", "MODE_BF16", "NORM_NONE", "NORM_UTIL", "NORM_FT",
+           "NORM_TORCH", "REDUCE_NONE", "REDUCE_MAX", "REDUCE_SUM"]

@@ -1,0 +1,702 @@
+// api.cu — the C ABI of libsss_b200.so (include/sss_b200.h): handles, workspaces and the wave driver
+// that strings scan -> expand -> refine -> emit together on the caller's stream.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sss_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sss {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  void* v = nullptr;
+  SSS_CUDA_OK(cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T)));
+  *p = (T*)v;
+  return 0;
+}
+template <typename T>
+static void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+// Workspace of one search call; grows monotonically.
+struct Workspace {
+  int64_t nq_pad = 0;
+  int cap = 0, d = 0, d_pad = 0, k = 0;
+  float *thr = nullptr, *margin = nullptr, *q_f32 = nullptr, *out_D = nullptr;
+  uint32_t *cnt = nullptr, *nret = nullptr;
+  uint64_t* cand = nullptr;
+  int* flags = nullptr;  // [0] overflow, [1] kernel watchdog
+  void* q_bf16 = nullptr;
+  int64_t* out_I = nullptr;
+  HitRecord* rec = nullptr;
+  uint32_t* rec_cnt = nullptr;
+  size_t rec_entries = 0;
+  int n_regions = 0;
+  int64_t out_elems = 0;
+
+  int ensure(int64_t nq_pad_, int cap_, int d_, int d_pad_, int64_t out_elems_) {
+    if (nq_pad_ > nq_pad || cap_ > cap || d_ != d || d_pad_ != d_pad) {
+      release_query_side();
+      nq_pad = std::max(nq_pad_, nq_pad);
+      cap = std::max(cap_, cap);
+      d = d_;
+      d_pad = d_pad_;
+      if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&cnt, nq_pad) ||
+          dev_alloc(&nret, nq_pad) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
+        return 1;
+      void* v = nullptr;
+      SSS_CUDA_OK(cudaMalloc(&v, (size_t)nq_pad * d_pad * 2));
+      q_bf16 = v;
+    }
+    if (!flags && dev_alloc(&flags, 2)) return 1;
+    if (out_elems_ > out_elems) {
+      dev_free(out_D);
+      dev_free(out_I);
+      out_elems = out_elems_;
+      if (dev_alloc(&out_D, out_elems) || dev_alloc(&out_I, out_elems)) return 1;
+    }
+    return 0;
+  }
+  int ensure_records(int n_regions_, int rec_cap) {
+    size_t need = (size_t)n_regions_ * rec_cap;
+    if (need > rec_entries) {
+      dev_free(rec);
+      rec_entries = need;
+      if (dev_alloc(&rec, rec_entries)) return 1;
+    }
+    if (n_regions_ > n_regions) {
+      dev_free(rec_cnt);
+      n_regions = n_regions_;
+      if (dev_alloc(&rec_cnt, n_regions)) return 1;
+    }
+    return 0;
+  }
+  void release_query_side() {
+    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(cand); dev_free(q_f32);
+    if (q_bf16) cudaFree(q_bf16);
+    q_bf16 = nullptr;
+  }
+  void release() {
+    release_query_side();
+    dev_free(flags); dev_free(out_D); dev_free(out_I); dev_free(rec); dev_free(rec_cnt);
+    nq_pad = 0; cap = 0; rec_entries = 0; n_regions = 0; out_elems = 0;
+  }
+  SelectState state() const {
+    SelectState s;
+    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.overflow = flags; s.cap = cap;
+    return s;
+  }
+};
+
+// A growable row store: fixed-order-normalised fp32 rows (rescoring / fp32 scan) and, when the tensor
+// path applies (d <= 128), a zero-padded bf16 copy laid out for TMA (row pitch d_pad*2 bytes).
+struct RowStore {
+  float* f32 = nullptr;
+  void* bf16 = nullptr;
+  unsigned int* maxnorm2 = nullptr;  // device, bits of max ||row||^2
+  int64_t n = 0, cap_rows = 0;
+  int ensure(int64_t rows, int d, int d_pad, bool want_bf16, cudaStream_t st) {
+    if (!maxnorm2) {
+      if (dev_alloc(&maxnorm2, 1)) return 1;
+      SSS_CUDA_OK(cudaMemsetAsync(maxnorm2, 0, sizeof(unsigned int), st));
+    }
+    if (rows <= cap_rows) return 0;
+    int64_t new_cap = std::max<int64_t>(rows, cap_rows + cap_rows / 2);
+    new_cap = (new_cap + 127) / 128 * 128;
+    float* nf = nullptr;
+    if (dev_alloc(&nf, (size_t)new_cap * d)) return 1;
+    if (n > 0) SSS_CUDA_OK(cudaMemcpyAsync(nf, f32, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    void* nb = nullptr;
+    if (want_bf16) {
+      SSS_CUDA_OK(cudaMalloc(&nb, (size_t)new_cap * d_pad * 2));
+      if (n > 0) SSS_CUDA_OK(cudaMemcpyAsync(nb, bf16, (size_t)n * d_pad * 2, cudaMemcpyDeviceToDevice, st));
+    }
+    SSS_CUDA_OK(cudaStreamSynchronize(st));
+    dev_free(f32);
+    if (bf16) cudaFree(bf16);
+    f32 = nf;
+    bf16 = nb;
+    cap_rows = new_cap;
+    return 0;
+  }
+  void release() {
+    dev_free(f32);
+    if (bf16) cudaFree(bf16);
+    bf16 = nullptr;
+    dev_free(maxnorm2);
+    n = cap_rows = 0;
+  }
+};
+
+}  // namespace sss
+
+using namespace sss;
+
+struct sss_index {
+  int device = 0, d = 0, d_pad = 0, metric = 0, num_sms = 148;
+  int64_t id_offset = 0;
+  bool tensor_ok = false;
+  RowStore rows;      // the added rows
+  RowStore sums;      // per-segment sums (reduce == SUM)
+  int reduce = 0;
+  int64_t n_seg = 0;
+  int64_t* seg_off = nullptr;  // device
+  int32_t* row_seg = nullptr;  // device
+  Workspace ws;
+  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0;
+  // optional scan-kernel timing (CUDA events on the launching stream around every scan launch)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double scan_us = 0.0;
+  int64_t scan_launches = 0;
+};
+
+extern "C" const char* sss_last_error(void) { return g_err.c_str(); }
+extern "C" int sss_version(void) { return 100; }
+extern "C" int sss_built_for_sm(void) { return 100; }
+
+extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric, int64_t id_offset) {
+  SSS_REQUIRE(out != nullptr, "sss_index_create: out is NULL");
+  SSS_REQUIRE(d >= 1, "sss_index_create: d must be >= 1");
+  SSS_REQUIRE(metric == SSS_METRIC_IP || metric == SSS_METRIC_L2, "Unregnozed metric");
+  int ndev = 0;
+  SSS_CUDA_OK(cudaGetDeviceCount(&ndev));
+  SSS_REQUIRE(device >= 0 && device < ndev, "sss_index_create: no such CUDA device");
+  cudaDeviceProp prop;
+  SSS_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  SSS_REQUIRE(prop.major == 10, "libsss_b200 is built for sm_100a only; device is sm_" +
+                                    std::to_string(prop.major * 10 + prop.minor));
+  sss_index* ix = new sss_index();
+  ix->device = device;
+  ix->d = d;
+  ix->d_pad = (d + 63) / 64 * 64;
+  ix->metric = metric;
+  ix->id_offset = id_offset;
+  ix->num_sms = prop.multiProcessorCount;
+  ix->tensor_ok = ix->d_pad <= 128 && metric == SSS_METRIC_IP;
+  *out = ix;
+  return 0;
+}
+
+extern "C" int sss_index_destroy(sss_index_t* ix) {
+  if (!ix) return 0;
+  DeviceGuard g(ix->device);
+  ix->rows.release();
+  ix->sums.release();
+  dev_free(ix->seg_off);
+  dev_free(ix->row_seg);
+  ix->ws.release();
+  for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+  delete ix;
+  return 0;
+}
+
+extern "C" int64_t sss_index_ntotal(const sss_index_t* ix) { return ix ? ix->rows.n : 0; }
+extern "C" int sss_index_dim(const sss_index_t* ix) { return ix ? ix->d : 0; }
+extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
+  if (!ix) return -1;
+  switch (what) {
+    case 0: return ix->stat_kernels;
+    case 1: return ix->stat_waves;
+    case 2: return ix->stat_reruns;
+    case 3: return (int64_t)(ix->scan_us * 1000.0);  // scan-kernel time of the last search, ns (profiling on)
+    case 4: return ix->scan_launches;
+    default: return -1;
+  }
+}
+extern "C" int sss_index_set_profiling(sss_index_t* ix, int on) {
+  SSS_REQUIRE(ix != nullptr, "sss_index_set_profiling: NULL index");
+  ix->profile = on != 0;
+  return 0;
+}
+
+extern "C" int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int rows_on_device, int norm_mode,
+                             void* stream) {
+  SSS_REQUIRE(ix != nullptr, "sss_index_add: NULL index");
+  SSS_REQUIRE(n >= 0, "sss_index_add: negative row count");
+  SSS_REQUIRE(norm_mode >= 0 && norm_mode <= 3, "sss_index_add: unknown norm_mode");
+  if (n == 0) return 0;
+  SSS_REQUIRE(rows != nullptr, "sss_index_add: NULL rows");
+  SSS_REQUIRE(ix->rows.n + n < 0xFFFFFFF0ll, "sss_index_add: more than 2^32 rows in one shard");
+  DeviceGuard g(ix->device);
+  SSS_REQUIRE(g.ok, "sss_index_add: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ix->rows.ensure(ix->rows.n + n, ix->d, ix->d_pad, ix->tensor_ok, st)) return 1;
+  const float* src = rows;
+  float* staged = nullptr;
+  if (!rows_on_device) {
+    if (dev_alloc(&staged, (size_t)n * ix->d)) return 1;
+    SSS_CUDA_OK(cudaMemcpyAsync(staged, rows, (size_t)n * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    src = staged;
+  }
+  int rc = launch_add_rows(src, n, ix->d, ix->d_pad, norm_mode, ix->rows.f32, ix->rows.bf16, ix->rows.n,
+                           ix->rows.maxnorm2, st);
+  if (staged) {
+    cudaStreamSynchronize(st);
+    cudaFree(staged);
+  }
+  if (rc) return rc;
+  ix->rows.n += n;
+  ix->reduce = 0;  // segments must be re-declared after adding rows
+  ix->n_seg = 0;
+  return 0;
+}
+
+extern "C" int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce) {
+  SSS_REQUIRE(ix != nullptr, "sss_index_set_segments: NULL index");
+  SSS_REQUIRE(reduce >= 0 && reduce <= 2, "sss_index_set_segments: unknown reduce");
+  DeviceGuard g(ix->device);
+  if (reduce == SSS_REDUCE_NONE) {
+    ix->reduce = 0;
+    ix->n_seg = 0;
+    return 0;
+  }
+  SSS_REQUIRE(seg_off != nullptr && n_seg >= 1, "sss_index_set_segments: need seg_off[n_seg+1]");
+  SSS_REQUIRE(seg_off[0] == 0 && seg_off[n_seg] == ix->rows.n, "sss_index_set_segments: seg_off must span [0, ntotal]");
+  for (int64_t s = 0; s < n_seg; ++s)
+    SSS_REQUIRE(seg_off[s + 1] >= seg_off[s], "sss_index_set_segments: seg_off must be non-decreasing");
+  dev_free(ix->seg_off);
+  dev_free(ix->row_seg);
+  if (dev_alloc(&ix->seg_off, n_seg + 1) || dev_alloc(&ix->row_seg, ix->rows.n)) return 1;
+  SSS_CUDA_OK(cudaMemcpy(ix->seg_off, seg_off, (size_t)(n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (launch_row_seg(ix->seg_off, n_seg, ix->row_seg, 0)) return 1;
+  if (reduce == SSS_REDUCE_SUM) {
+    // linearity: sum_r <q, x_r> = <q, sum_r x_r>; build the summed rows once, then search them as rows
+    ix->sums.release();
+    if (ix->sums.ensure(n_seg, ix->d, ix->d_pad, ix->tensor_ok, 0)) return 1;
+    float* tmp = nullptr;
+    if (dev_alloc(&tmp, (size_t)n_seg * ix->d)) return 1;
+    int rc = launch_segment_sum(ix->rows.f32, ix->seg_off, n_seg, ix->d, tmp, 0);
+    if (!rc) rc = launch_add_rows(tmp, n_seg, ix->d, ix->d_pad, 0, ix->sums.f32, ix->sums.bf16, 0, ix->sums.maxnorm2, 0);
+    cudaStreamSynchronize(0);
+    cudaFree(tmp);
+    if (rc) return rc;
+    ix->sums.n = n_seg;
+  }
+  SSS_CUDA_OK(cudaStreamSynchronize(0));
+  ix->reduce = reduce;
+  ix->n_seg = n_seg;
+  return 0;
+}
+
+namespace sss {
+
+// Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
+// waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
+static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe) {
+  std::vector<int64_t> ends;
+  int64_t first = std::max<int64_t>(128, (std::min<int64_t>(cap / 2, cap - k) / 128) * 128);
+  if (first > 2048) first = 2048;
+  int64_t e = std::min(n_rows, first);
+  ends.push_back(e);
+  while (e < n_rows) {
+    int64_t step = safe ? first : (e < 262144 ? 3 * e : e);
+    e = std::min(n_rows, e + step);
+    ends.push_back(e);
+  }
+  return ends;
+}
+
+struct BatchArgs {
+  const float* q;
+  int64_t nq;
+  int k, mode;
+  bool q_on_device, out_on_device;
+  float* D;
+  int64_t* I;
+};
+
+static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
+  const bool use_sums = ix->reduce == SSS_REDUCE_SUM;
+  RowStore& rs = use_sums ? ix->sums : ix->rows;
+  const int64_t n_rows = rs.n;
+  int mode = b.mode;
+  if (mode != SSS_MODE_FP32 && !ix->tensor_ok) {
+    SSS_REQUIRE(mode == SSS_MODE_EXACT,
+                "SSS_MODE_BF16 needs d <= 128 and the inner-product metric (use SSS_MODE_EXACT or SSS_MODE_FP32)");
+    mode = SSS_MODE_FP32;  // EXACT is defined as "bit-identical to FP32": run the fp32 scan itself
+  }
+  const bool tensor = mode != SSS_MODE_FP32 && n_rows > 0;
+  int cap = 4096;
+  while (cap < 4 * b.k && cap < 8192) cap *= 2;
+  SSS_REQUIRE(b.k <= cap / 2, "k too large (max 4096)");
+  const int64_t nq_pad = (b.nq + 127) / 128 * 128;
+  Workspace& ws = ix->ws;
+  if (ws.ensure(nq_pad, cap, ix->d, ix->d_pad, b.out_on_device ? 0 : b.nq * b.k)) return 1;
+  const float* qdev = b.q;
+  if (!b.q_on_device) {
+    SSS_CUDA_OK(cudaMemcpyAsync(ws.q_f32, b.q, (size_t)b.nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    qdev = ws.q_f32;
+  }
+  float* Ddev = b.out_on_device ? b.D : ws.out_D;
+  int64_t* Idev = b.out_on_device ? b.I : ws.out_I;
+
+  Bf16ScanPlan plan;
+  alignas(64) unsigned char tmap_q[128], tmap_db[128];
+  if (tensor) {
+    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, &plan)) return 1;
+    if (ws.ensure_records(plan.n_regions, plan.rec_cap)) return 1;
+    if (make_tensor_map_bf16_2d(tmap_q, ws.q_bf16, (uint64_t)nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
+    if (make_tensor_map_bf16_2d(tmap_db, rs.bf16, (uint64_t)n_rows, (uint64_t)ix->d_pad, 128)) return 1;
+  }
+  // |fp32 fixed-order score - tensor-core score| <= eps * ||q|| * max||x||: bf16 input rounding
+  // (2 * 2^-8 + 2^-16) plus fp32 accumulation slack of both sides.
+  const float eps = mode == SSS_MODE_EXACT ? (0.0078125f * 1.01f + (float)ix->d * 2.4e-7f) : 0.0f;
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    SelectState state = ws.state();
+    state.cap = cap;
+    if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr, eps, rs.maxnorm2, state,
+                            st))
+      return 1;
+    SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
+    ix->stat_kernels += 1;
+    RefineArgs ra;
+    ra.nq = b.nq;
+    ra.k = b.k;
+    ra.reduce_max = ix->reduce == SSS_REDUCE_MAX;
+    ra.row_seg = ix->row_seg;
+    ra.rescore = mode == SSS_MODE_EXACT;
+    ra.db_f32 = rs.f32;
+    ra.q_f32 = qdev;
+    ra.d = ix->d;
+    ra.metric = ix->metric;
+    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1);
+    int64_t begin = 0;
+    for (int64_t end : ends) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (ix->profile) {
+        while (ix->ev.size() < ix->ev_used + 2) {
+          cudaEvent_t e;
+          SSS_CUDA_OK(cudaEventCreate(&e));
+          ix->ev.push_back(e);
+        }
+        e0 = ix->ev[ix->ev_used++];
+        e1 = ix->ev[ix->ev_used++];
+        SSS_CUDA_OK(cudaEventRecord(e0, st));
+      }
+      if (tensor) {
+        if (launch_scan_bf16(plan, tmap_q, tmap_db, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st)) return 1;
+        if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
+        if (launch_expand_records(ws.rec, ws.rec_cnt, plan.n_regions, plan.rec_cap, n_rows, state, st)) return 1;
+        ix->stat_kernels += 2;
+      } else {
+        if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, qdev, b.nq, state, st)) return 1;
+        if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
+        ix->stat_kernels += 1;
+      }
+      if (launch_refine(ra, state, st)) return 1;
+      ix->stat_kernels += 1;
+      ix->stat_waves += 1;
+      begin = end;
+    }
+    if (launch_emit(state, b.nq, b.k, ix->metric, ix->id_offset, Ddev, Idev, st)) return 1;
+    ix->stat_kernels += 1;
+    int flags[2] = {0, 0};
+    SSS_CUDA_OK(cudaMemcpyAsync(flags, ws.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    if (!b.out_on_device) {
+      SSS_CUDA_OK(cudaMemcpyAsync(b.D, Ddev, (size_t)b.nq * b.k * sizeof(float), cudaMemcpyDeviceToHost, st));
+      SSS_CUDA_OK(cudaMemcpyAsync(b.I, Idev, (size_t)b.nq * b.k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    SSS_CUDA_OK(cudaStreamSynchronize(st));
+    if (ix->profile) {
+      for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+        float ms = 0.0f;
+        SSS_CUDA_OK(cudaEventElapsedTime(&ms, ix->ev[i], ix->ev[i + 1]));
+        ix->scan_us += (double)ms * 1000.0;
+        ix->scan_launches += 1;
+      }
+      ix->ev_used = 0;
+    }
+    SSS_REQUIRE(flags[1] == 0, "tensor-core scan watchdog fired (barrier code " + std::to_string(flags[1]) + ")");
+    if (flags[0] == 0) return 0;
+    // a candidate list or record region overflowed (adversarial score order): redo with waves that
+    // cannot overflow by construction
+    SSS_REQUIRE(attempt == 0, "candidate overflow persisted in the safe wave schedule (internal error)");
+    ix->stat_reruns += 1;
+  }
+  return 0;
+}
+
+}  // namespace sss
+
+extern "C" int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
+                                float* D, int64_t* I, int out_on_device, void* stream) {
+  SSS_REQUIRE(ix != nullptr, "sss_index_search: NULL index");
+  SSS_REQUIRE(k >= 1, "sss_index_search: k must be >= 1");
+  SSS_REQUIRE(nq >= 0, "sss_index_search: negative nq");
+  SSS_REQUIRE(mode >= 0 && mode <= 2, "sss_index_search: unknown mode");
+  if (nq == 0) return 0;
+  SSS_REQUIRE(q && D && I, "sss_index_search: NULL buffer");
+  DeviceGuard g(ix->device);
+  SSS_REQUIRE(g.ok, "sss_index_search: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  ix->stat_kernels = ix->stat_waves = ix->stat_reruns = 0;
+  ix->scan_us = 0.0;
+  ix->scan_launches = 0;
+  const int64_t QB = 2048;  // queries per pass: <= 16 resident m-tile groups, grid_x >= 37
+  for (int64_t q0 = 0; q0 < nq; q0 += QB) {
+    BatchArgs b;
+    b.nq = std::min(QB, nq - q0);
+    b.q = q + q0 * ix->d;
+    b.k = k;
+    b.mode = mode;
+    b.q_on_device = q_on_device != 0;
+    b.out_on_device = out_on_device != 0;
+    b.D = D + q0 * k;
+    b.I = I + q0 * k;
+    if (search_batch(ix, b, st)) return 1;
+  }
+  return 0;
+}
+
+extern "C" int sss_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, int on_device, int device,
+                             void* stream) {
+  SSS_REQUIRE(in && out, "sss_normalize: NULL buffer");
+  SSS_REQUIRE(n >= 0 && d >= 1, "sss_normalize: bad shape");
+  SSS_REQUIRE(norm_mode >= 0 && norm_mode <= 3, "sss_normalize: unknown norm_mode");
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  SSS_REQUIRE(g.ok, "sss_normalize: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (on_device) return launch_normalize(in, out, n, d, norm_mode, st);
+  float* tmp = nullptr;
+  if (dev_alloc(&tmp, (size_t)n * d)) return 1;
+  int rc = 0;
+  if (cudaMemcpyAsync(tmp, in, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = 1;
+  if (!rc) rc = launch_normalize(tmp, tmp, n, d, norm_mode, st);
+  if (!rc && cudaMemcpyAsync(out, tmp, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+  cudaFree(tmp);
+  if (rc && g_err.empty()) set_error("sss_normalize: CUDA copy failed");
+  return rc;
+}
+
+extern "C" int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_shards, int64_t nq, int k, int metric,
+                              float* D, int64_t* I, int device, void* stream) {
+  SSS_REQUIRE(cand_D && cand_I && D && I, "sss_topk_merge: NULL buffer");
+  SSS_REQUIRE(n_shards >= 1 && k >= 1 && nq >= 0, "sss_topk_merge: bad shape");
+  DeviceGuard g(device);
+  SSS_REQUIRE(g.ok, "sss_topk_merge: cudaSetDevice failed");
+  return launch_topk_merge(cand_D, cand_I, n_shards, nq, k, metric, D, I, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// binary index
+// ---------------------------------------------------------------------------------------------------
+namespace sss {
+__global__ void repack_codes_kernel(const uint8_t* __restrict__ in, int nbytes, uint8_t* __restrict__ out, int pitch,
+                                    int64_t n) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * pitch) return;
+  int64_t r = t / pitch;
+  int b = (int)(t % pitch);
+  out[t] = b < nbytes ? in[r * nbytes + b] : (uint8_t)0;
+}
+static int launch_repack(const uint8_t* in, int nbytes, uint8_t* out, int pitch, int64_t n, cudaStream_t st) {
+  int64_t total = n * pitch;
+  if (total <= 0) return 0;
+  repack_codes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nbytes, out, pitch, n);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+}  // namespace sss
+
+struct sss_binary_index {
+  int device = 0, nbits = 0, nbytes = 0, pitch = 0;
+  int64_t id_offset = 0;
+  uint8_t* codes = nullptr;  // [cap_rows, pitch]
+  int64_t n = 0, cap_rows = 0;
+  Workspace ws;
+  uint8_t* q_codes = nullptr;
+  int64_t q_cap = 0;
+  int32_t* out_D = nullptr;
+  int64_t out_elems = 0;
+};
+
+extern "C" int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset) {
+  SSS_REQUIRE(out != nullptr, "sss_binary_create: out is NULL");
+  SSS_REQUIRE(nbits >= 8 && nbits % 8 == 0 && nbits <= 512, "sss_binary_create: nbits must be a multiple of 8, <= 512");
+  int ndev = 0;
+  SSS_CUDA_OK(cudaGetDeviceCount(&ndev));
+  SSS_REQUIRE(device >= 0 && device < ndev, "sss_binary_create: no such CUDA device");
+  sss_binary_index* ix = new sss_binary_index();
+  ix->device = device;
+  ix->nbits = nbits;
+  ix->nbytes = nbits / 8;
+  ix->pitch = (ix->nbytes + 3) / 4 * 4;
+  ix->id_offset = id_offset;
+  *out = ix;
+  return 0;
+}
+
+extern "C" int sss_binary_destroy(sss_binary_index_t* ix) {
+  if (!ix) return 0;
+  DeviceGuard g(ix->device);
+  dev_free(ix->codes);
+  dev_free(ix->q_codes);
+  dev_free(ix->out_D);
+  ix->ws.release();
+  delete ix;
+  return 0;
+}
+
+extern "C" int64_t sss_binary_ntotal(const sss_binary_index_t* ix) { return ix ? ix->n : 0; }
+
+extern "C" int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream) {
+  SSS_REQUIRE(ix != nullptr, "sss_binary_add: NULL index");
+  SSS_REQUIRE(n >= 0, "sss_binary_add: negative row count");
+  if (n == 0) return 0;
+  SSS_REQUIRE(codes != nullptr, "sss_binary_add: NULL codes");
+  DeviceGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ix->n + n > ix->cap_rows) {
+    int64_t new_cap = std::max<int64_t>(ix->n + n, ix->cap_rows + ix->cap_rows / 2);
+    uint8_t* nc = nullptr;
+    if (dev_alloc(&nc, (size_t)new_cap * ix->pitch)) return 1;
+    if (ix->n > 0) SSS_CUDA_OK(cudaMemcpyAsync(nc, ix->codes, (size_t)ix->n * ix->pitch, cudaMemcpyDeviceToDevice, st));
+    SSS_CUDA_OK(cudaStreamSynchronize(st));
+    dev_free(ix->codes);
+    ix->codes = nc;
+    ix->cap_rows = new_cap;
+  }
+  const uint8_t* src = codes;
+  uint8_t* staged = nullptr;
+  if (!on_device) {
+    if (dev_alloc(&staged, (size_t)n * ix->nbytes)) return 1;
+    SSS_CUDA_OK(cudaMemcpyAsync(staged, codes, (size_t)n * ix->nbytes, cudaMemcpyHostToDevice, st));
+    src = staged;
+  }
+  int rc = launch_repack(src, ix->nbytes, ix->codes + (size_t)ix->n * ix->pitch, ix->pitch, n, st);
+  if (staged) {
+    cudaStreamSynchronize(st);
+    cudaFree(staged);
+  }
+  if (rc) return rc;
+  ix->n += n;
+  return 0;
+}
+
+extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64_t nq, int k, int q_on_device,
+                                 int32_t* D, int64_t* I, int out_on_device, void* stream) {
+  SSS_REQUIRE(ix != nullptr, "sss_binary_search: NULL index");
+  SSS_REQUIRE(k >= 1 && nq >= 0, "sss_binary_search: bad k / nq");
+  if (nq == 0) return 0;
+  SSS_REQUIRE(q && D && I, "sss_binary_search: NULL buffer");
+  DeviceGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int cap = 4096;
+  while (cap < 4 * k && cap < 8192) cap *= 2;
+  SSS_REQUIRE(k <= cap / 2, "k too large (max 4096)");
+  const int64_t nq_pad = (nq + 127) / 128 * 128;
+  Workspace& ws = ix->ws;
+  if (ws.ensure(nq_pad, cap, 1, 64, out_on_device ? 0 : nq * k)) return 1;
+  if (nq > ix->q_cap) {
+    dev_free(ix->q_codes);
+    ix->q_cap = nq;
+    if (dev_alloc(&ix->q_codes, (size_t)nq * ix->pitch)) return 1;
+  }
+  if (!out_on_device && nq * k > ix->out_elems) {
+    dev_free(ix->out_D);
+    ix->out_elems = nq * k;
+    if (dev_alloc(&ix->out_D, ix->out_elems)) return 1;
+  }
+  const uint8_t* qsrc = q;
+  uint8_t* staged = nullptr;
+  if (!q_on_device) {
+    if (dev_alloc(&staged, (size_t)nq * ix->nbytes)) return 1;
+    SSS_CUDA_OK(cudaMemcpyAsync(staged, q, (size_t)nq * ix->nbytes, cudaMemcpyHostToDevice, st));
+    qsrc = staged;
+  }
+  int rc = launch_repack(qsrc, ix->nbytes, ix->q_codes, ix->pitch, nq, st);
+  int32_t* Ddev = out_on_device ? D : ix->out_D;
+  int64_t* Idev = out_on_device ? I : ws.out_I;
+  for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
+    SelectState state = ws.state();
+    state.cap = cap;
+    rc = launch_prep_queries(nullptr, 0, nq_pad, 1, 64, nullptr, 0.0f, nullptr, state, st);
+    // prep marks every row as padding (nq = 0): reopen the real queries
+    if (!rc) {
+      std::vector<float> neg((size_t)nq, -INFINITY);
+      if (cudaMemcpyAsync(ws.thr, neg.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("sss_binary_search: threshold reset failed");
+        rc = 1;
+      }
+    }
+    RefineArgs ra;
+    ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
+    ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
+    std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
+    int64_t begin = 0;
+    for (int64_t end : ends) {
+      if (rc) break;
+      rc = launch_scan_hamming(ix->codes, ix->pitch, begin, end, ix->q_codes, nq, state, st);
+      if (!rc) rc = launch_refine(ra, state, st);
+      begin = end;
+    }
+    if (!rc) rc = launch_emit_hamming(state, nq, k, ix->nbits, ix->id_offset, Ddev, Idev, st);
+    int flag = 0;
+    if (!rc && cudaMemcpyAsync(&flag, ws.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+    if (!rc && !out_on_device) {
+      if (cudaMemcpyAsync(D, Ddev, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(I, Idev, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = 1;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+    if (rc || flag == 0) break;
+    if (attempt == 1) {
+      set_error("candidate overflow persisted in the safe wave schedule (internal error)");
+      rc = 1;
+    }
+  }
+  if (staged) cudaFree(staged);
+  if (rc && g_err.empty()) set_error("sss_binary_search: CUDA failure");
+  return rc;
+}
+
+extern "C" int sss_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits_in, int on_device, int device,
+                                  void* stream) {
+  SSS_REQUIRE(x && codes, "sss_pack_sign_bits: NULL buffer");
+  SSS_REQUIRE(n >= 0 && nbits_in >= 1, "sss_pack_sign_bits: bad shape");
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (on_device) return launch_pack_sign_bits(x, codes, n, nbits_in, st);
+  const int nbytes = (nbits_in + 7) / 8;
+  float* dx = nullptr;
+  uint8_t* dc = nullptr;
+  if (dev_alloc(&dx, (size_t)n * nbits_in) || dev_alloc(&dc, (size_t)n * nbytes)) return 1;
+  int rc = 0;
+  if (cudaMemcpyAsync(dx, x, (size_t)n * nbits_in * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = 1;
+  if (!rc) rc = launch_pack_sign_bits(dx, dc, n, nbits_in, st);
+  if (!rc && cudaMemcpyAsync(codes, dc, (size_t)n * nbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+  cudaFree(dx);
+  cudaFree(dc);
+  if (rc && g_err.empty()) set_error("sss_pack_sign_bits: CUDA failure");
+  return rc;
+}

@@ -1,0 +1,69 @@
+// kernels.h — host-side launchers of every kernel in libsss_b200 (all return 0 / non-zero + set_error).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sss {
+
+// prep.cu
+int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
+                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st);
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, float eps,
+                        const unsigned int* maxnorm2_bits, SelectState st, cudaStream_t stream);
+int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st);
+int launch_segment_sum(const float* rows, const int64_t* seg_off, int64_t n_seg, int d, float* out, cudaStream_t st);
+int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, cudaStream_t st);
+
+// scan_fp32.cu — CUDA-core fixed-order scan of rows [row_begin, row_end)
+int launch_scan_fp32(const float* db, int d, int metric, int64_t row_begin, int64_t row_end, const float* q, int64_t nq,
+                     SelectState st, cudaStream_t stream);
+
+// scan_bf16_sm100.cu — TMA + tcgen05 scan of rows [row_begin, row_end) (row_begin multiple of 128)
+struct Bf16ScanPlan {
+  int num_kb;       // 64-wide K blocks (d_pad / 64)
+  int num_mt;       // resident query m-tiles per CTA (1..4)
+  int total_mtiles; // m-tiles of the whole padded query batch
+  int num_stages;   // DB tile ring depth
+  int grid_x;       // CTAs along the DB
+  int grid_y;       // CTA groups along the queries
+  int smem_bytes;
+  int rec_cap;      // hit records per epilogue warp
+  int n_regions;    // grid_x * grid_y * 8 epilogue warps
+};
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan);
+// tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
+int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
+int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, int64_t row_begin,
+                     int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt, int* err_flag,
+                     cudaStream_t stream);
+
+// select.cu
+int launch_expand_records(const HitRecord* rec, const uint32_t* rec_cnt, int n_regions, int rec_cap, int64_t row_limit,
+                          SelectState st, cudaStream_t stream);
+struct RefineArgs {
+  int64_t nq;
+  int k;
+  int reduce_max;            // dedupe new entries by segment, keep the best
+  const int32_t* row_seg;    // [n_rows] when reduce_max
+  int rescore;               // recompute new entries' scores in fixed-order fp32
+  const float* db_f32;       // [n_rows, d] when rescore
+  const float* q_f32;        // [nq, d] when rescore
+  int d;
+  int metric;
+};
+int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream);
+int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
+                cudaStream_t stream);
+int launch_topk_merge(const float* cD, const int64_t* cI, int n_shards, int64_t nq, int k, int metric, float* D,
+                      int64_t* I, cudaStream_t stream);
+
+// binary.cu
+int launch_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits, cudaStream_t st);
+int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_t row_end, const uint8_t* q, int64_t nq,
+                        SelectState st, cudaStream_t stream);
+int launch_emit_hamming(SelectState st, int64_t nq, int k, int nbits, int64_t id_offset, int32_t* D, int64_t* I,
+                        cudaStream_t stream);
+
+}  // namespace sss

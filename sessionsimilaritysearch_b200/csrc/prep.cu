@@ -1,0 +1,156 @@
+// prep.cu — HBM-bound staging kernels: row normalisation + bf16 packing (index.add), query staging,
+// segment maps and segment sums.  Replaces normalize() (util_amazon_filtered.py:28-31,
+// fine_tune_ours.py:38-40) and the numpy side of build_index (test_amazon_filterd.py:207-223).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sss {
+
+// Rows are staged through shared memory so that global reads and writes are fully coalesced while the
+// sum of squares is still accumulated by ONE thread per row in k-ascending order (the oracle's order).
+__global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__ in, int64_t n, int d, int d_pad,
+                                                       int norm_mode, int rows_per_block, float* __restrict__ out_f32,
+                                                       __nv_bfloat16* __restrict__ out_bf16, int64_t out_row0,
+                                                       unsigned int* __restrict__ maxnorm2_bits) {
+  extern __shared__ float smem[];
+  const int ld = d + 1;
+  float* den = smem + (size_t)rows_per_block * ld;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int nrows = (int)min((int64_t)rows_per_block, n - row0);
+  const int tid = threadIdx.x;
+  const int total = nrows * d;
+  const float* src = in + row0 * (int64_t)d;
+  for (int i = tid; i < total; i += blockDim.x) smem[(i / d) * ld + (i % d)] = src[i];
+  __syncthreads();
+  if (tid < nrows) {
+    const float* x = smem + tid * ld;
+    float ss = 0.0f;
+    for (int j = 0; j < d; ++j) ss = __fmaf_rn(x[j], x[j], ss);
+    float dn = 1.0f, n2 = ss;
+    if (norm_mode == 1) {
+      dn = __fsqrt_rn(ss < 1e-6f ? 1e-6f : ss);
+    } else if (norm_mode == 2) {
+      dn = __fadd_rn(__fsqrt_rn(ss), 1e-4f);
+    } else if (norm_mode == 3) {
+      float nn = __fsqrt_rn(ss);
+      dn = nn < 1e-12f ? 1e-12f : nn;
+    }
+    if (norm_mode != 0) n2 = ss / (dn * dn);
+    den[tid] = dn;
+    if (maxnorm2_bits) atomicMax(maxnorm2_bits, __float_as_uint(n2 * 1.00002f + 1e-30f));
+  }
+  __syncthreads();
+  if (out_f32) {
+    float* dst = out_f32 + (out_row0 + row0) * (int64_t)d;
+    for (int i = tid; i < total; i += blockDim.x) {
+      int r = i / d, j = i % d;
+      float v = smem[r * ld + j];
+      dst[i] = norm_mode == 0 ? v : __fdiv_rn(v, den[r]);
+    }
+  }
+  if (out_bf16) {
+    __nv_bfloat16* dstb = out_bf16 + (out_row0 + row0) * (int64_t)d_pad;
+    const int totalp = nrows * d_pad;
+    for (int i = tid; i < totalp; i += blockDim.x) {
+      int r = i / d_pad, j = i % d_pad;
+      float v = 0.0f;
+      if (j < d) {
+        v = smem[r * ld + j];
+        if (norm_mode != 0) v = __fdiv_rn(v, den[r]);
+      }
+      dstb[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
+                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int rpb = (int)(60 * 1024 / (sizeof(float) * (d + 1)));
+  if (rpb > 128) rpb = 128;
+  if (rpb < 1) rpb = 1;
+  size_t smem = sizeof(float) * ((size_t)rpb * (d + 1) + rpb);
+  SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for add_rows_kernel");
+  SSS_CUDA_OK(cudaFuncSetAttribute(add_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (n + rpb - 1) / rpb;
+  add_rows_kernel<<<(unsigned)blocks, 128, smem, st>>>(in, n, d, d_pad, norm_mode, rpb, out_f32,
+                                                        (__nv_bfloat16*)out_bf16, out_row0, maxnorm2_bits);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Query staging: bf16 copy (zero padded to [nq_pad, d_pad]), filter slack, selection state reset.
+// One warp per query row.
+__global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad, int d, int d_pad,
+                                    __nv_bfloat16* __restrict__ q_bf16, float eps, const unsigned int* maxnorm2_bits,
+                                    SelectState st) {
+  const int warps_per_block = blockDim.x / 32;
+  const int64_t row = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= nq_pad) return;
+  float ss = 0.0f;
+  for (int j = lane; j < d_pad; j += 32) {
+    float v = (row < nq && j < d) ? q[row * (int64_t)d + j] : 0.0f;
+    ss += v * v;
+    if (q_bf16) q_bf16[row * (int64_t)d_pad + j] = __float2bfloat16_rn(v);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) {
+    float mx = maxnorm2_bits ? __uint_as_float(*maxnorm2_bits) : 0.0f;
+    // |exact - tensor-core score| <= eps * ||q|| * max||x|| (Cauchy-Schwarz on the bf16 input rounding)
+    st.margin[row] = eps > 0.0f ? eps * sqrtf(ss * 1.00002f) * sqrtf(mx) + 1e-30f : 0.0f;
+    st.thr[row] = row < nq ? -INFINITY : INFINITY;
+    st.cnt[row] = 0;
+    st.nret[row] = 0;
+    if (row == 0) *st.overflow = 0;
+  }
+}
+
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, float eps,
+                        const unsigned int* maxnorm2_bits, SelectState st, cudaStream_t stream) {
+  const int wpb = 8;
+  int64_t blocks = (nq_pad + wpb - 1) / wpb;
+  prep_queries_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(q, nq, nq_pad, d, d_pad, (__nv_bfloat16*)q_bf16,
+                                                                  eps, maxnorm2_bits, st);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// row -> segment map (segments are short: one thread per segment)
+__global__ void row_seg_kernel(const int64_t* __restrict__ seg_off, int64_t n_seg, int32_t* __restrict__ row_seg) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  for (int64_t r = seg_off[s]; r < seg_off[s + 1]; ++r) row_seg[r] = (int32_t)s;
+}
+int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st) {
+  if (n_seg <= 0) return 0;
+  row_seg_kernel<<<(unsigned)((n_seg + 255) / 256), 256, 0, st>>>(seg_off, n_seg, row_seg);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// per-segment sum of rows, rows added in row order (SUM reduction is linear: <q, sum x_r> )
+__global__ void segment_sum_kernel(const float* __restrict__ rows, const int64_t* __restrict__ seg_off, int64_t n_seg,
+                                   int d, float* __restrict__ out) {
+  int64_t s = blockIdx.x;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float acc = 0.0f;
+    for (int64_t r = seg_off[s]; r < seg_off[s + 1]; ++r) acc = __fadd_rn(acc, rows[r * (int64_t)d + j]);
+    out[s * (int64_t)d + j] = acc;
+  }
+}
+int launch_segment_sum(const float* rows, const int64_t* seg_off, int64_t n_seg, int d, float* out, cudaStream_t st) {
+  if (n_seg <= 0) return 0;
+  segment_sum_kernel<<<(unsigned)n_seg, 128, 0, st>>>(rows, seg_off, n_seg, d, out);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// stand-alone normalize() (device in/out, may alias)
+int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, cudaStream_t st) {
+  return launch_add_rows(in, n, d, d, norm_mode, out, nullptr, 0, nullptr, st);
+}
+
+}  // namespace sss

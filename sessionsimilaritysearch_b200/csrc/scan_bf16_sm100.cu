@@ -1,0 +1,409 @@
+// scan_bf16_sm100.cu — the fused tensor-core scan: Q x DB^T on tcgen05 (bf16 in, fp32 accumulate in
+// TMEM), operands staged by TMA, and the streaming top-k FILTER fused into the epilogue so that the score
+// matrix never leaves the SM.  Replaces the sgemm + heap inside faiss IndexFlatIP.search
+// (test_amazon_filterd.py:211-214,578; fine_tune_ours.py:848-849,882).
+//
+// Shape of one CTA (persistent, 1 CTA per SM, 384 threads):
+//   warp 0 lane 0   TMA producer: loads its resident query m-tiles once, then streams DB tiles
+//                   (128 rows x d_pad bf16, SWIZZLE_128B, one 16 KB box per 64-wide K block) through an
+//                   mbarrier ring.
+//   warp 1 lane 0   MMA issuer: for every DB tile and every resident m-tile, num_kb*4 tcgen05.mma
+//                   (M=128 queries, N=128 rows, K=16) into one of four 128-column TMEM slots; commits
+//                   to the slot's "full" barrier, and to the stage's "empty" barrier after the last m-tile.
+//   warp 2          TMEM allocator (512 columns).
+//   warps 4-11      two epilogue warpgroups (slots 0/2 and 1/3).  A thread owns ONE query (TMEM lane):
+//                   tcgen05.ld 32 columns -> 3-input max tree -> one compare against the query's running
+//                   threshold.  Only when some lane of the warp sees max > thr does the warp take the slow
+//                   path: those lanes dump their 32 raw scores as a 144-byte HitRecord into the warp's
+//                   private record region (slot index from a ballot — no atomics).  expand/refine
+//                   (select.cu) turn records into exact top-k lists and tighter thresholds between waves.
+//
+// Arithmetic intensity: a CTA holding num_mt*128 resident queries does 2*num_mt*128*128*d_pad flop per
+// 128*d_pad*2 bytes of DB tile, i.e. num_mt*128 flop/byte — 512 flop/B at num_mt=4, well above the B200
+// ridge (~210-250 flop/B), so the kernel is tensor-bound for >= ~256 resident queries and HBM-bound (DB
+// stream) below.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sss {
+
+namespace {
+
+constexpr int kKBlockBytes = kTileRows * 128;  // one 128-row x 64-col bf16 box = 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kNumThreads = 384;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kBarrierBytes = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s
+      atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileRows >> 3) << 17) |
+                            ((uint32_t)(kTileQ >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+struct ScanParams {
+  int num_kb, num_mt, num_stages;
+  int total_mtiles;      // over the whole (padded) query batch
+  int64_t row_begin;     // multiple of 128
+  int64_t n_tiles;       // DB tiles in this wave
+  SelectState st;
+  HitRecord* rec;
+  uint32_t* rec_cnt;
+  int rec_cap;
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                 const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int mt_base = blockIdx.y * p.num_mt;
+  const int num_mt = min(p.num_mt, p.total_mtiles - mt_base);
+  const int n_tiles = (int)p.n_tiles;
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  const uint32_t q_smem = smem_base;
+  const uint32_t db_smem = q_smem + (uint32_t)(p.num_mt * p.num_kb) * kKBlockBytes;
+  const uint32_t bar_base = db_smem + (uint32_t)(p.num_stages * p.num_kb) * kKBlockBytes;
+  const uint32_t full_bar = bar_base;                         // [kMaxStages]
+  const uint32_t empty_bar = bar_base + 8 * kMaxStages;       // [kMaxStages]
+  const uint32_t tfull_bar = bar_base + 16 * kMaxStages;      // [4]
+  const uint32_t tempty_bar = tfull_bar + 32;                 // [4]
+  const uint32_t qfull_bar = tempty_bar + 32;                 // [1]
+  const uint32_t tmem_ptr_addr = qfull_bar + 8;
+  // generic pointer to the TMEM base slot for the post-alloc read
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_db);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp of the owning warpgroup
+    }
+    mbar_init(qfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_expect_tx(qfull_bar, (uint32_t)(num_mt * p.num_kb) * kKBlockBytes);
+      for (int mt = 0; mt < num_mt; ++mt)
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(q_smem + (uint32_t)(mt * p.num_kb + kb) * kKBlockBytes, &tmap_q, qfull_bar, kb * 64,
+                      (mt_base + mt) * kTileQ);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 101);
+        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.num_kb * kKBlockBytes);
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int row = (int)p.row_begin + tile * kTileRows;
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes, &tmap_db, full_bar + 8 * stage,
+                      kb * 64, row);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(qfull_bar, 0, p.err_flag, 102);
+      tc_fence_after();
+      uint32_t u = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 103);
+        tc_fence_after();
+        for (int mt = 0; mt < num_mt; ++mt, ++u) {
+          const uint32_t slot = u & 3u;
+          mbar_wait(tempty_bar + 8 * slot, ((u >> 2) & 1u) ^ 1u, p.err_flag, 104);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * (uint32_t)kTileRows;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const uint64_t adesc = umma_desc_sw128(q_smem + (uint32_t)(mt * p.num_kb + kb) * kKBlockBytes);
+            const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K=16 bf16 = 32 bytes) inside the 128-byte swizzle row
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(tfull_bar + 8 * slot);
+        }
+        umma_commit(empty_bar + 8 * stage);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: fused top-k filter =====================
+    const int ew = warp - 4;
+    const int wg = ew >> 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const uint32_t region = (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (uint32_t)ew;
+    HitRecord* myrec = p.rec + (size_t)region * p.rec_cap;
+    uint32_t wcount = 0;
+    const int total_units = my_tiles * num_mt;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // unit u = (tile iteration it, resident m-tile mt); this warpgroup takes u = wg, wg+2, ...
+    int it = 0, mt = wg;
+    while (mt >= num_mt) { mt -= num_mt; ++it; }
+    for (int u = wg; u < total_units; u += 2) {
+      const uint32_t slot = (uint32_t)(u & 3);
+      const uint32_t ph = (uint32_t)((u >> 2) & 1);
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const uint32_t qidx = (uint32_t)((mt_base + mt) * kTileQ + quarter * 32 + lane);
+      const float thr = p.st.thr[qidx];
+      const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * kTileRows);
+      mt += 2;
+      while (mt >= num_mt) { mt -= num_mt; ++it; }
+      mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 105);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (uint32_t)kTileRows;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (c == 3) {  // accumulators are in registers: hand the TMEM slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+        }
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+        float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]);
+        float m2 = max3(f[6], f[7], f[8]), m3 = max3(f[9], f[10], f[11]);
+        m0 = max3(m0, f[12], f[13]); m1 = max3(m1, f[14], f[15]);
+        m2 = max3(m2, f[16], f[17]); m3 = max3(m3, f[18], f[19]);
+        m0 = max3(m0, f[20], f[21]); m1 = max3(m1, f[22], f[23]);
+        m2 = max3(m2, f[24], f[25]); m3 = max3(m3, f[26], f[27]);
+        m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
+        const float mx = fmaxf(max3(m0, m1, m2), m3);
+        const bool hit = mx > thr;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (bal != 0u) {
+          if (hit) {
+            const uint32_t idx = wcount + __popc(bal & lt_mask);
+            if (idx < (uint32_t)p.rec_cap) {
+              uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
+              dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[1 + i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+          }
+          wcount += __popc(bal);
+        }
+      }
+    }
+    if (lane == 0) p.rec_cnt[region] = wcount;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SSS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  SSS_REQUIRE(cols_pad % 64 == 0, "bf16 operand width must be padded to a multiple of 64");
+  SSS_REQUIRE(((uintptr_t)base & 127) == 0, "bf16 operand base must be 128-byte aligned");
+  cuuint64_t dims[2] = {cols_pad, rows};
+  cuuint64_t strides[1] = {cols_pad * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn((CUtensorMap*)out_map128, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
+  SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 128, "tensor-core scan supports d <= 128");
+  SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
+  const int total_mtiles = (int)(nq_pad / kTileQ);
+  plan->num_kb = d_pad / 64;
+  plan->total_mtiles = total_mtiles;
+  plan->grid_y = (total_mtiles + 3) / 4;
+  plan->num_mt = (total_mtiles + plan->grid_y - 1) / plan->grid_y;
+  plan->grid_x = num_sms / plan->grid_y;
+  if (plan->grid_x < 1) plan->grid_x = 1;
+  const int q_bytes = plan->num_mt * plan->num_kb * kKBlockBytes;
+  const int stage_bytes = plan->num_kb * kKBlockBytes;
+  const int avail = 227 * 1024 - 1024 - kBarrierBytes - q_bytes;
+  int stages = avail / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  SSS_REQUIRE(stages >= 2, "not enough shared memory for the DB tile ring");
+  plan->num_stages = stages;
+  plan->smem_bytes = 1024 + q_bytes + stages * stage_bytes + kBarrierBytes;
+  plan->rec_cap = 1024;
+  plan->n_regions = plan->grid_x * plan->grid_y * 8;
+  return 0;
+}
+
+int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, int64_t row_begin,
+                     int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt, int* err_flag,
+                     cudaStream_t stream) {
+  SSS_REQUIRE(row_begin % kTileRows == 0, "scan wave must start on a 128-row boundary");
+  ScanParams p;
+  p.num_kb = plan.num_kb;
+  p.num_mt = plan.num_mt;
+  p.num_stages = plan.num_stages;
+  p.total_mtiles = plan.total_mtiles;
+  p.row_begin = row_begin;
+  p.n_tiles = (row_end - row_begin + kTileRows - 1) / kTileRows;
+  p.st = st;
+  p.rec = rec;
+  p.rec_cnt = rec_cnt;
+  p.rec_cap = plan.rec_cap;
+  p.err_flag = err_flag;
+  if (p.n_tiles <= 0) return 0;
+  static int smem_set = 0;
+  if (smem_set < plan.smem_bytes) {
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    smem_set = plan.smem_bytes;
+  }
+  dim3 grid(plan.grid_x, plan.grid_y);
+  scan_bf16_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_q,
+                                                                   *(const CUtensorMap*)tmap_db, p);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sss

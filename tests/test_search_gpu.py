@@ -1,0 +1,232 @@
+"""GPU parity tests of the retrieval path, through the Python facade -> C ABI -> CUDA kernels, against the
+CPU oracle (oracle/search_oracle.c, O2) on the same seeded inputs.
+
+Bars (BASELINE.json north_star): fp32 and exact modes bit-exact ids AND scores vs O2 (ties by id);
+bf16 mode |score - O1| <= 1e-3 and recall@k >= 0.999.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_clustered, make_iid, make_segments, make_session_rows, make_ties
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sss():
+    import sessionsimilaritysearch_b200 as m
+    return m
+
+
+def _assert_exact(D, I, Do, Io):
+    assert np.array_equal(I, Io), "ids differ at %s" % (np.argwhere(I != Io)[:5],)
+    assert np.array_equal(D.view(np.uint32), Do.view(np.uint32)), "scores differ bitwise"
+
+
+@pytest.mark.parametrize("d", [7, 128, 200, 1600])
+def test_normalize_bit_exact_and_golden(sss, oracle, d):
+    import os
+    x = make_iid(37, d, 100 + d)
+    x[0] *= 1e-5
+    x[1] = 0
+    for mode in (sss.NORM_UTIL, sss.NORM_FT, sss.NORM_TORCH, sss.NORM_NONE):
+        got = sss.normalize(x, mode)
+        assert np.array_equal(got.view(np.uint32), oracle.normalize(x, mode).view(np.uint32))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "normalize_golden.npz"))
+    key = "d%d" % d
+    if "in_" + key in gold:
+        np.testing.assert_allclose(sss.normalize(gold["in_" + key], sss.NORM_UTIL), gold["util_" + key], rtol=2e-6,
+                                   atol=1e-9)
+        np.testing.assert_allclose(sss.normalize(gold["in_" + key], sss.NORM_FT), gold["ft_" + key], rtol=2e-6,
+                                   atol=1e-9)
+    v = make_iid(1, d, 5)[0]
+    assert np.array_equal(sss.normalize(v, sss.NORM_UTIL), oracle.normalize(v[None], sss.NORM_UTIL)[0])
+    assert np.allclose(sss.normalize(np.ones(4)), 0.5)  # test_amazon_filterd.py:866
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+@pytest.mark.parametrize("d", [7, 64, 100, 128, 200])
+def test_flat_ip_bit_exact(sss, oracle, mode, d):
+    db = make_iid(20000, d, 1)
+    q = make_iid(33, d, 2)
+    ix = sss.build_index(db, 'cos', mode=mode)
+    qn = sss.normalize(q)
+    D, I = ix.search(qn, 100)
+    dbn = oracle.normalize(db, oracle.NORM_UTIL)
+    Do, Io = oracle.search_flat(dbn, oracle.normalize(q, oracle.NORM_UTIL), 100)
+    _assert_exact(D, I, Do, Io)
+    assert ix.ntotal == 20000 and ix.stats()["reruns"] == 0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_flat_ip_raw_unnormalised(sss, oracle, mode):
+    db = make_iid(30000, 128, 3) * 3.0
+    q = make_iid(130, 128, 4) * 0.5
+    ix = sss.build_index(db, 'ip', mode=mode)
+    D, I = ix.search(q, 10)
+    Do, Io = oracle.search_flat(db, q, 10)
+    _assert_exact(D, I, Do, Io)
+
+
+def test_bf16_mode_tolerance_and_recall(sss, oracle):
+    db = make_clustered(200000, 128, 5)
+    q = make_clustered(64, 128, 6)
+    ix = sss.build_index(db, 'cos', mode="bf16")
+    D, I = ix.search(sss.normalize(q), 100)
+    Do, Io = oracle.search_blas(oracle.normalize_util_numpy(db), oracle.normalize_util_numpy(q), 100)  # O1
+    recall = np.mean([len(set(I[r]) & set(Io[r])) / 100.0 for r in range(q.shape[0])])
+    # scores of the ids both lists share agree within 1e-3 absolute
+    for r in range(q.shape[0]):
+        common = {i: s for i, s in zip(Io[r], Do[r])}
+        for i, s in zip(I[r], D[r]):
+            if i in common:
+                assert abs(float(s) - float(common[i])) <= 1e-3
+    assert np.all(np.diff(D, axis=1) <= 0)
+    # rank-wise scores within tolerance as well
+    assert np.max(np.abs(D - Do)) <= 1e-3
+    assert recall >= 0.999, "bf16 recall@100 vs O1 = %.5f" % recall
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+@pytest.mark.parametrize("d", [64, 128, 256])
+def test_tie_heavy_is_ordered_by_id(sss, oracle, mode, d):
+    db = make_ties(50000, d, 7)
+    q = make_ties(40, d, 8)
+    ix = sss.build_index(db, 'ip', mode=mode)
+    D, I = ix.search(q, 100)
+    Do, Io = oracle.search_flat(db, q, 100)
+    _assert_exact(D, I, Do, Io)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_l2(sss, oracle, mode):
+    db = make_iid(20000, 96, 9)
+    q = make_iid(17, 96, 10)
+    ix = sss.build_index(db, 'l2', mode=mode)
+    D, I = ix.search(q, 50)
+    Do, Io = oracle.search_flat(db, q, 50, metric=oracle.METRIC_L2)
+    _assert_exact(D, I, Do, Io)
+    assert np.all(np.diff(D, axis=1) >= 0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+@pytest.mark.parametrize("reduce", ["max", "sum"])
+def test_segment_reduce(sss, oracle, mode, reduce):
+    seg = make_segments(60000, 11)
+    db = make_session_rows(seg, 128, 12)
+    q = make_iid(50, 128, 13)
+    ix = sss.build_index(db, 'cos', mode=mode)
+    ix.set_segments(seg, reduce)
+    D, I = ix.search(sss.normalize(q), 100)
+    Do, Io = oracle.search_flat(oracle.normalize(db, oracle.NORM_UTIL), oracle.normalize(q, oracle.NORM_UTIL), 100,
+                                seg_off=seg, reduce={"max": 1, "sum": 2}[reduce])
+    _assert_exact(D, I, Do, Io)
+    assert I.max() < len(seg) - 1
+    ix.set_segments(None, None)
+    D, I = ix.search(sss.normalize(q), 10)
+    Do, Io = oracle.search_flat(oracle.normalize(db, oracle.NORM_UTIL), oracle.normalize(q, oracle.NORM_UTIL), 10)
+    _assert_exact(D, I, Do, Io)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact", "bf16"])
+def test_edge_shapes(sss, oracle, mode):
+    db = make_iid(300, 128, 14)
+    q = make_iid(3, 128, 15)
+    ix = sss.IndexFlatIP(128, mode=mode)
+    # empty index: all padding
+    D, I = ix.search(q, 5)
+    assert np.all(I == -1) and np.all(np.isneginf(D))
+    ix.add(db[:40])
+    ix.add(db[40:41])       # ragged adds
+    ix.add(db[41:300])
+    assert ix.ntotal == 300
+    D, I = ix.search(q, 400)  # k > ntotal
+    Do, Io = oracle.search_flat(db, q, 400)
+    assert np.array_equal(I[:, 300:], Io[:, 300:]) and np.all(I[:, 300:] == -1)
+    if mode != "bf16":
+        _assert_exact(D, I, Do, Io)
+    else:
+        assert np.mean(I[:, :300] == Io[:, :300]) > 0.9
+    D, I = ix.search(q[:1], 1)  # nq = 1, k = 1
+    assert I[0, 0] == Io[0, 0]
+    D0, I0 = ix.search(q[:0], 3)  # no queries
+    assert D0.shape == (0, 3) and I0.shape == (0, 3)
+
+
+def test_query_batches_over_the_pass_limit(sss, oracle):
+    db = make_iid(5000, 64, 16)
+    q = make_iid(2500, 64, 17)  # > 2048: two passes
+    ix = sss.build_index(db, 'ip', mode="exact")
+    D, I = ix.search(q, 7)
+    Do, Io = oracle.search_flat(db, q, 7)
+    _assert_exact(D, I, Do, Io)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_adversarial_order_takes_the_safe_schedule(sss, oracle, mode):
+    # scores grow with the row id: every later row beats the running threshold, lists overflow, and the
+    # driver must fall back to waves that cannot overflow — results stay exact.
+    rng = np.random.default_rng(18)
+    u = rng.standard_normal(128).astype(np.float32)
+    u /= np.linalg.norm(u)
+    n = 30000
+    db = (np.linspace(0.1, 1.0, n, dtype=np.float32)[:, None] * u[None, :]).astype(np.float32)
+    db += 1e-4 * rng.standard_normal(db.shape).astype(np.float32)
+    q = (u[None, :] + 0.01 * rng.standard_normal((5, 128))).astype(np.float32)
+    ix = sss.build_index(db, 'ip', mode=mode)
+    D, I = ix.search(q, 100)
+    Do, Io = oracle.search_flat(db, q, 100)
+    _assert_exact(D, I, Do, Io)
+    assert ix.stats()["reruns"] >= 1
+
+
+def test_million_rows_exact_equals_fp32_and_oracle_sample(sss, oracle):
+    db = make_clustered(1000000, 128, 19)
+    q = make_clustered(1000, 128, 20)
+    ix = sss.build_index(db, 'cos', mode="exact")
+    qn = sss.normalize(q)
+    D, I = ix.search(qn, 100)
+    D2, I2 = ix.search(qn, 100, mode="fp32")
+    _assert_exact(D, I, D2, I2)
+    sub = np.arange(0, 1000, 125)
+    Do, Io = oracle.search_flat(oracle.normalize(db, oracle.NORM_UTIL), oracle.normalize(q[sub], oracle.NORM_UTIL), 100)
+    _assert_exact(D[sub], I[sub], Do, Io)
+    Db, Ib = ix.search(qn, 100, mode="bf16")
+    recall = np.mean([len(set(Ib[r]) & set(I[r])) / 100.0 for r in range(1000)])
+    assert recall >= 0.999 and np.max(np.abs(Db - D)) <= 1e-3, recall
+
+
+def test_torch_device_tensors(sss, oracle):
+    import torch
+    db = make_iid(10000, 128, 21)
+    q = make_iid(20, 128, 22)
+    ix = sss.IndexFlatIP(128)
+    ix.add(torch.from_numpy(db).cuda(), norm=sss.NORM_UTIL)
+    qn = sss.normalize(torch.from_numpy(q).cuda())
+    D, I = ix.search(qn, 10)
+    assert D.is_cuda and I.is_cuda and I.dtype == torch.int64
+    Do, Io = oracle.search_flat(oracle.normalize(db, 1), oracle.normalize(q, 1), 10)
+    _assert_exact(D.cpu().numpy(), I.cpu().numpy(), Do, Io)
+
+
+def test_unknown_metric_raises_like_the_reference(sss):
+    with pytest.raises(RuntimeError):
+        sss.build_index(make_iid(10, 8, 0), 'cosine')
+
+
+def test_binary_hamming(sss, oracle):
+    rng = np.random.default_rng(23)
+    x = np.sign(rng.standard_normal((40000, 250))).astype(np.float32)
+    x[rng.random(x.shape) < 0.02] = 0
+    codes = sss.pack_sign_bits(x)
+    assert np.array_equal(codes, np.packbits(((x + 1) / 2).astype(int), axis=1))
+    qx = x[:25].copy()
+    flip = rng.random(qx.shape) < 0.1
+    qx[flip] *= -1
+    qcodes = sss.pack_sign_bits(qx)
+    ix = sss.IndexBinaryFlat(codes.shape[1] * 8)
+    ix.add(codes)
+    D, I = ix.search(qcodes, 100)
+    Do, Io = oracle.search_hamming(codes, qcodes, 100)
+    assert D.dtype == np.int32 and np.array_equal(D, Do) and np.array_equal(I, Io)
+    assert ix.ntotal == 40000
