@@ -264,6 +264,9 @@ def main():
     def step_e2e():
         return index.search(q_np, a.k)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # sampled from the warm-up on: every sample is under load
     for _ in range(a.warmup):
         step_dev()
     inner.set_profiling(True)
@@ -276,11 +279,7 @@ def main():
         scan_ns[1] += st["scan_launches"]
         return r
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms_total = timed(step_dev_prof, a.steps)
-    clocks = sampler.stop() if rank == 0 else None
     inner.set_profiling(False)
     kernels_per_step = inner.stats()["kernels"] + (1 if world > 1 else 0)
     waves = inner.stats()["waves"]
@@ -288,6 +287,7 @@ def main():
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / a.steps
     value = a.nq / (ms_step * 1e-3)

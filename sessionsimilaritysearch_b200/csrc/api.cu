@@ -398,7 +398,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         e1 = ix->ev[ix->ev_used++];
         SSS_CUDA_OK(cudaEventRecord(e0, st));
       }
-      if (tensor) {
+      // The first wave has no threshold: every score is a candidate.  In EXACT mode it is cheaper to get those
+      // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
+      const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0);
+      ra.rescore = mode == SSS_MODE_EXACT && wave_tensor;
+      if (wave_tensor) {
         if (launch_scan_bf16(plan, tmap_q, tmap_db, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st)) return 1;
         if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
         if (launch_expand_records(ws.rec, ws.rec_cnt, plan.n_regions, plan.rec_cap, n_rows, state, st)) return 1;
@@ -409,7 +413,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         ix->stat_kernels += 1;
       }
       if (launch_refine(ra, state, st)) return 1;
-      ix->stat_kernels += 1;
+      ix->stat_kernels += ra.rescore ? 2 : 1;
       ix->stat_waves += 1;
       begin = end;
     }

@@ -53,6 +53,8 @@ struct RefineArgs {
   int d;
   int metric;
 };
+int launch_rescore(const RefineArgs& a, SelectState st, cudaStream_t stream);
+// rescore (when a.rescore) + reduce/sort/truncate + threshold update
 int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream);
 int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
                 cudaStream_t stream);

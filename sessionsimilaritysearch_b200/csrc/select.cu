@@ -14,31 +14,34 @@
 namespace sss {
 
 // ---- expand: tensor-core hit records -> per-query candidate lists -----------------------------------
-__global__ void expand_records_kernel(const HitRecord* __restrict__ rec, const uint32_t* __restrict__ rec_cnt,
-                                      int rec_cap, int64_t row_limit, SelectState st) {
+__global__ void __launch_bounds__(128) expand_records_kernel(const HitRecord* __restrict__ rec,
+                                                             const uint32_t* __restrict__ rec_cnt, int rec_cap,
+                                                             int64_t row_limit, SelectState st) {
   const int region = blockIdx.x;
   uint32_t n = rec_cnt[region];
   if (n > (uint32_t)rec_cap) {
-    if (threadIdx.x == 0 && blockIdx.y == 0) *st.overflow = 1;
+    if (threadIdx.x == 0) *st.overflow = 1;
     n = rec_cap;
   }
-  const uint32_t e = blockIdx.y * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  const HitRecord* r = rec + (size_t)region * rec_cap + e;
-  const uint32_t q = r->q;
-  const uint32_t row_base = r->row_base;
-  const float thr = st.thr[q];
-  const float4* v4 = reinterpret_cast<const float4*>(r->v);
+  // 4 threads per record: each takes 8 of the 32 scores (two float4 loads)
+  const int sub = threadIdx.x & 3;
+  for (uint32_t e = threadIdx.x >> 2; e < n; e += blockDim.x >> 2) {
+    const HitRecord* r = rec + (size_t)region * rec_cap + e;
+    const uint32_t q = r->q;
+    const uint32_t row_base = r->row_base + sub * 8;
+    const float thr = st.thr[q];
+    const float4* v4 = reinterpret_cast<const float4*>(r->v) + sub * 2;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float4 v = v4[c];
-    float vv[4] = {v.x, v.y, v.z, v.w};
+    for (int c = 0; c < 2; ++c) {
+      float4 v = v4[c];
+      float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int64_t row = (int64_t)row_base + c * 4 + t;
-      if (vv[t] > thr && row < row_limit) {
-        uint32_t slot = atomicAdd(&st.cnt[q], 1u);
-        if (slot < (uint32_t)st.cap) st.cand[(size_t)q * st.cap + slot] = pack_cand(score_key(vv[t]), (uint32_t)row);
+      for (int t = 0; t < 4; ++t) {
+        const int64_t row = (int64_t)row_base + c * 4 + t;
+        if (vv[t] > thr && row < row_limit) {
+          uint32_t slot = atomicAdd(&st.cnt[q], 1u);
+          if (slot < (uint32_t)st.cap) st.cand[(size_t)q * st.cap + slot] = pack_cand(score_key(vv[t]), (uint32_t)row);
+        }
       }
     }
   }
@@ -46,8 +49,74 @@ __global__ void expand_records_kernel(const HitRecord* __restrict__ rec, const u
 
 int launch_expand_records(const HitRecord* rec, const uint32_t* rec_cnt, int n_regions, int rec_cap, int64_t row_limit,
                           SelectState st, cudaStream_t stream) {
-  dim3 grid(n_regions, (rec_cap + 127) / 128);
-  expand_records_kernel<<<grid, 128, 0, stream>>>(rec, rec_cnt, rec_cap, row_limit, st);
+  expand_records_kernel<<<n_regions, 128, 0, stream>>>(rec, rec_cnt, rec_cap, row_limit, st);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- rescore: exact fixed-order fp32 score of every NEW candidate (EXACT mode) ------------------------
+// One block per query, 8 warps.  A warp takes 32 new candidates at a time: their rows are read with fully
+// coalesced 128-byte requests (one row segment per request, lane = column) into a warp-private shared tile,
+// then lane l walks ITS row in k-ascending order with a single accumulator — the same rounding sequence as
+// the fp32 scan and the oracle — and rewrites the candidate's key in place.
+constexpr int RS_WARPS = 8;
+constexpr int RS_KC = 32;  // columns staged per round
+__global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(RefineArgs a, SelectState st) {
+  extern __shared__ float rs_smem[];
+  float* qs = rs_smem;                                    // [d_round] the query
+  const int d_round = (a.d + RS_KC - 1) / RS_KC * RS_KC;
+  float* tiles = rs_smem + d_round;                       // [RS_WARPS][32][RS_KC + 1]
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = st.cnt[q];
+  const int n = c > (uint32_t)st.cap ? st.cap : (int)c;
+  const int nr = (int)st.nret[q];
+  if (n <= nr) return;
+  for (int j = threadIdx.x; j < d_round; j += blockDim.x) qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
+  __syncthreads();
+  uint64_t* g = st.cand + (size_t)q * st.cap;
+  float* tile = tiles + (size_t)warp * 32 * (RS_KC + 1);
+  for (int base = nr + warp * 32; base < n; base += RS_WARPS * 32) {
+    const int i = base + lane;
+    const uint64_t v = i < n ? g[i] : 0ull;
+    const uint32_t my_row = i < n ? cand_id(v) : 0u;
+    float acc = 0.0f;
+    for (int k0 = 0; k0 < a.d; k0 += RS_KC) {
+      const int col = k0 + lane;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+        tile[r * (RS_KC + 1) + lane] = col < a.d ? a.db_f32[(size_t)row * a.d + col] : 0.0f;
+      }
+      __syncwarp();
+      const float* mine = tile + lane * (RS_KC + 1);
+      if (a.metric == 0) {
+#pragma unroll
+        for (int kk = 0; kk < RS_KC; ++kk) acc = __fmaf_rn(qs[k0 + kk], mine[kk], acc);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < RS_KC; ++kk) {
+          // padded columns: q = x = 0 -> t = 0 -> acc unchanged
+          const float t = __fsub_rn(qs[k0 + kk], mine[kk]);
+          acc = __fmaf_rn(t, t, acc);
+        }
+      }
+      __syncwarp();
+    }
+    if (i < n) g[i] = pack_cand(score_key(a.metric == 0 ? acc : -acc), my_row);
+  }
+}
+
+int launch_rescore(const RefineArgs& a, SelectState st, cudaStream_t stream) {
+  const int d_round = (a.d + RS_KC - 1) / RS_KC * RS_KC;
+  size_t smem = sizeof(float) * ((size_t)d_round + (size_t)RS_WARPS * 32 * (RS_KC + 1));
+  SSS_REQUIRE(smem <= 96 * 1024, "embedding width too large for rescore_kernel");
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    SSS_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  rescore_kernel<<<(unsigned)a.nq, RS_WARPS * 32, smem, stream>>>(a, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -86,29 +155,9 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs a, SelectState s
   int P = 2;
   while (P < n) P <<= 1;
   uint64_t* g = st.cand + (size_t)q * cap;
-  const float* qv = a.rescore ? a.q_f32 + (size_t)q * a.d : nullptr;
   for (int i = tid; i < P; i += blockDim.x) {
     uint64_t v = i < n ? g[i] : 0ull;
-    if (i >= nr && i < n) {
-      uint32_t row = cand_id(v);
-      uint32_t key = cand_key(v);
-      if (a.rescore) {
-        const float* x = a.db_f32 + (size_t)row * a.d;
-        float acc = 0.0f;
-        if (a.metric == 0) {
-          for (int j = 0; j < a.d; ++j) acc = __fmaf_rn(qv[j], x[j], acc);
-        } else {
-          for (int j = 0; j < a.d; ++j) {
-            float t = __fsub_rn(qv[j], x[j]);
-            acc = __fmaf_rn(t, t, acc);
-          }
-          acc = -acc;
-        }
-        key = score_key(acc);
-      }
-      uint32_t id = a.reduce_max ? (uint32_t)a.row_seg[row] : row;
-      v = pack_cand(key, id);
-    }
+    if (a.reduce_max && i >= nr && i < n) v = pack_cand(cand_key(v), (uint32_t)a.row_seg[cand_id(v)]);
     e[i] = v;
   }
   if (tid == 0) s_m = 0;
@@ -151,6 +200,7 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineArgs a, SelectState s
 }
 
 int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream) {
+  if (a.rescore && launch_rescore(a, st, stream)) return 1;
   size_t smem = (size_t)st.cap * sizeof(uint64_t);
   SSS_REQUIRE(st.cap <= 8192, "candidate capacity too large for refine_kernel");
   static bool attr_done = false;
