@@ -45,7 +45,7 @@ struct Workspace {
   int64_t nq_pad = 0;
   int cap = 0, d = 0, d_pad = 0, k = 0;
   float *thr = nullptr, *margin = nullptr, *q_f32 = nullptr, *out_D = nullptr;
-  uint32_t *cnt = nullptr, *nret = nullptr;
+  uint32_t *cnt = nullptr, *nret = nullptr, *done = nullptr;
   uint64_t* cand = nullptr;
   int* flags = nullptr;  // [0] overflow, [1] kernel watchdog
   void* q_bf16 = nullptr;
@@ -64,7 +64,7 @@ struct Workspace {
       d = d_;
       d_pad = d_pad_;
       if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&cnt, nq_pad) ||
-          dev_alloc(&nret, nq_pad) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
+          dev_alloc(&nret, nq_pad) || dev_alloc(&done, nq_pad) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
         return 1;
       void* v = nullptr;
       SSS_CUDA_OK(cudaMalloc(&v, (size_t)nq_pad * d_pad * 2));
@@ -94,7 +94,7 @@ struct Workspace {
     return 0;
   }
   void release_query_side() {
-    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(cand); dev_free(q_f32);
+    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(done); dev_free(cand); dev_free(q_f32);
     if (q_bf16) cudaFree(q_bf16);
     q_bf16 = nullptr;
   }
@@ -105,7 +105,8 @@ struct Workspace {
   }
   SelectState state() const {
     SelectState s;
-    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.overflow = flags; s.cap = cap;
+    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.done = done; s.overflow = flags;
+    s.cap = cap;
     return s;
   }
 };
@@ -115,12 +116,12 @@ struct Workspace {
 struct RowStore {
   float* f32 = nullptr;
   void* bf16 = nullptr;
-  unsigned int* maxnorm2 = nullptr;  // device, bits of max ||row||^2
+  unsigned int* maxnorm2 = nullptr;  // device [2]: bits of max ||row||^2 and of max ||row - bf16(row)||^2
   int64_t n = 0, cap_rows = 0;
   int ensure(int64_t rows, int d, int d_pad, bool want_bf16, cudaStream_t st) {
     if (!maxnorm2) {
-      if (dev_alloc(&maxnorm2, 1)) return 1;
-      SSS_CUDA_OK(cudaMemsetAsync(maxnorm2, 0, sizeof(unsigned int), st));
+      if (dev_alloc(&maxnorm2, 2)) return 1;
+      SSS_CUDA_OK(cudaMemsetAsync(maxnorm2, 0, 2 * sizeof(unsigned int), st));
     }
     if (rows <= cap_rows) return 0;
     int64_t new_cap = std::max<int64_t>(rows, cap_rows + cap_rows / 2);
@@ -306,14 +307,16 @@ namespace sss {
 
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
-static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe) {
+static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups = false) {
   std::vector<int64_t> ends;
   int64_t first = std::max<int64_t>(128, (std::min<int64_t>(cap / 2, cap - k) / 128) * 128);
   if (first > 2048) first = 2048;
   int64_t e = std::min(n_rows, first);
   ends.push_back(e);
   while (e < n_rows) {
-    int64_t step = safe ? first : (e < 262144 ? 3 * e : e);
+    // rows of one session pass the filter together, so session-reduced searches see several candidate rows
+    // per new session: keep those waves to a doubling
+    int64_t step = safe ? first : ((e < 262144 && !dense_groups) ? 3 * e : e);
     e = std::min(n_rows, e + step);
     ends.push_back(e);
   }
@@ -340,9 +343,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     mode = SSS_MODE_FP32;  // EXACT is defined as "bit-identical to FP32": run the fp32 scan itself
   }
   const bool tensor = mode != SSS_MODE_FP32 && n_rows > 0;
-  int cap = 4096;
-  while (cap < 4 * b.k && cap < 8192) cap *= 2;
-  SSS_REQUIRE(b.k <= cap / 2, "k too large (max 4096)");
+  const int cap = 4096;
+  SSS_REQUIRE(b.k <= cap / 2, "k too large (max 2048)");
   const int64_t nq_pad = (b.nq + 127) / 128 * 128;
   Workspace& ws = ix->ws;
   if (ws.ensure(nq_pad, cap, ix->d, ix->d_pad, b.out_on_device ? 0 : b.nq * b.k)) return 1;
@@ -362,15 +364,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     if (make_tensor_map_bf16_2d(tmap_q, ws.q_bf16, (uint64_t)nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
     if (make_tensor_map_bf16_2d(tmap_db, rs.bf16, (uint64_t)n_rows, (uint64_t)ix->d_pad, 128)) return 1;
   }
-  // |fp32 fixed-order score - tensor-core score| <= eps * ||q|| * max||x||: bf16 input rounding
-  // (2 * 2^-8 + 2^-16) plus fp32 accumulation slack of both sides.
-  const float eps = mode == SSS_MODE_EXACT ? (0.0078125f * 1.01f + (float)ix->d * 2.4e-7f) : 0.0f;
-
   for (int attempt = 0; attempt < 2; ++attempt) {
     SelectState state = ws.state();
     state.cap = cap;
-    if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr, eps, rs.maxnorm2, state,
-                            st))
+    if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr,
+                            mode == SSS_MODE_EXACT ? 1 : 0, rs.maxnorm2, state, st))
       return 1;
     SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
     ix->stat_kernels += 1;
@@ -384,8 +382,9 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     ra.q_f32 = qdev;
     ra.d = ix->d;
     ra.metric = ix->metric;
-    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1);
+    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, ix->reduce == SSS_REDUCE_MAX);
     int64_t begin = 0;
+    uint32_t wave_id = 0;
     for (int64_t end : ends) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (ix->profile) {
@@ -402,18 +401,22 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
       const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0);
       ra.rescore = mode == SSS_MODE_EXACT && wave_tensor;
+      ra.wave = ++wave_id;
+      ra.rec = wave_tensor ? ws.rec : nullptr;
+      ra.rec_cnt = ws.rec_cnt;
+      ra.rec_nsub = tensor ? plan.grid_x * 2 : 0;
+      ra.row_limit = n_rows;
       if (wave_tensor) {
         if (launch_scan_bf16(plan, tmap_q, tmap_db, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st)) return 1;
         if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
-        if (launch_expand_records(ws.rec, ws.rec_cnt, plan.n_regions, plan.rec_cap, n_rows, state, st)) return 1;
-        ix->stat_kernels += 2;
+        ix->stat_kernels += 1;
       } else {
         if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, qdev, b.nq, state, st)) return 1;
         if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
         ix->stat_kernels += 1;
       }
       if (launch_refine(ra, state, st)) return 1;
-      ix->stat_kernels += ra.rescore ? 2 : 1;
+      ix->stat_kernels += b.k <= 512 ? 2 : 1;
       ix->stat_waves += 1;
       begin = end;
     }
@@ -612,9 +615,8 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
   SSS_REQUIRE(q && D && I, "sss_binary_search: NULL buffer");
   DeviceGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
-  int cap = 4096;
-  while (cap < 4 * k && cap < 8192) cap *= 2;
-  SSS_REQUIRE(k <= cap / 2, "k too large (max 4096)");
+  const int cap = 4096;
+  SSS_REQUIRE(k <= cap / 2, "k too large (max 2048)");
   const int64_t nq_pad = (nq + 127) / 128 * 128;
   Workspace& ws = ix->ws;
   if (ws.ensure(nq_pad, cap, 1, 64, out_on_device ? 0 : nq * k)) return 1;
@@ -641,7 +643,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
   for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
     SelectState state = ws.state();
     state.cap = cap;
-    rc = launch_prep_queries(nullptr, 0, nq_pad, 1, 64, nullptr, 0.0f, nullptr, state, st);
+    rc = launch_prep_queries(nullptr, 0, nq_pad, 1, 64, nullptr, 0, nullptr, state, st);
     // prep marks every row as padding (nq = 0): reopen the real queries
     if (!rc) {
       std::vector<float> neg((size_t)nq, -INFINITY);
@@ -654,10 +656,12 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     RefineArgs ra;
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
+    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.row_limit = ix->n;
     std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
     int64_t begin = 0;
     for (int64_t end : ends) {
       if (rc) break;
+      ra.wave += 1;
       rc = launch_scan_hamming(ix->codes, ix->pitch, begin, end, ix->q_codes, nq, state, st);
       if (!rc) rc = launch_refine(ra, state, st);
       begin = end;

@@ -61,11 +61,15 @@ struct SelectState {
   uint32_t* nret;    // [nq_pad] entries [0, nret) are retained (already reduced) from earlier waves
   uint64_t* cand;    // [nq_pad, cap]
   float* margin;     // [nq_pad] filter slack of the bf16 scan in EXACT mode, else 0
+  uint32_t* done;    // [nq_pad] id of the last wave whose refine has processed this query
   int* overflow;     // [1] set when any list / record region overflowed
   int cap;
 };
 
 // Tensor-core scan hit record: one epilogue lane saw max(32 consecutive scores) > thr and dumped them.
+// Records of query q written by scan CTA x (blockIdx.x) and epilogue warpgroup w live in the private
+// sub-region ((q * grid_x + x) * 2 + w) of kRecSubCap records: no atomics on the producer side, and refine
+// finds a query's records without a scatter pass.
 struct __align__(16) HitRecord {
   uint32_t q;         // query index (padded space)
   uint32_t row_base;  // DB row of v[0]
@@ -74,6 +78,7 @@ struct __align__(16) HitRecord {
 };
 static_assert(sizeof(HitRecord) == 144, "HitRecord must be 9 x 16 bytes");
 
+constexpr int kRecSubCap = 16;   // records per (query, scan CTA, epilogue warpgroup) and wave
 constexpr int kTileRows = 128;   // DB rows per tensor-core tile (UMMA N)
 constexpr int kTileQ = 128;      // queries per m-tile (UMMA M)
 

@@ -10,8 +10,9 @@ namespace sss {
 // prep.cu
 int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
                     int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st);
-int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, float eps,
-                        const unsigned int* maxnorm2_bits, SelectState st, cudaStream_t stream);
+// stats[0] = bits of max ||row||^2, stats[1] = bits of max ||row - bf16(row)||^2 (both from launch_add_rows)
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
+                        const unsigned int* stats, SelectState st, cudaStream_t stream);
 int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st);
 int launch_segment_sum(const float* rows, const int64_t* seg_off, int64_t n_seg, int d, float* out, cudaStream_t st);
 int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, cudaStream_t st);
@@ -40,8 +41,6 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
                      cudaStream_t stream);
 
 // select.cu
-int launch_expand_records(const HitRecord* rec, const uint32_t* rec_cnt, int n_regions, int rec_cap, int64_t row_limit,
-                          SelectState st, cudaStream_t stream);
 struct RefineArgs {
   int64_t nq;
   int k;
@@ -52,9 +51,13 @@ struct RefineArgs {
   const float* q_f32;        // [nq, d] when rescore
   int d;
   int metric;
+  uint32_t wave;             // id of this wave (st.done bookkeeping), > 0
+  const HitRecord* rec;      // tensor-core hit records of this wave, or nullptr for list input
+  const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
+  int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
+  int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill
 };
-int launch_rescore(const RefineArgs& a, SelectState st, cudaStream_t stream);
-// rescore (when a.rescore) + reduce/sort/truncate + threshold update
+// group by session, (EXACT) prune + re-score survivors, keep the best k, raise the threshold
 int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream);
 int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
                 cudaStream_t stream);

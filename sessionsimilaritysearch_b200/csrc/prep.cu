@@ -39,7 +39,17 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
     }
     if (norm_mode != 0) n2 = ss / (dn * dn);
     den[tid] = dn;
-    if (maxnorm2_bits) atomicMax(maxnorm2_bits, __float_as_uint(n2 * 1.00002f + 1e-30f));
+    if (maxnorm2_bits) {
+      // ||x - bf16(x)||^2 of the stored row: the exact rounding error the tensor-core scan will see
+      float e2 = 0.0f;
+      for (int j = 0; j < d; ++j) {
+        const float y = norm_mode == 0 ? x[j] : __fdiv_rn(x[j], dn);
+        const float r = y - __bfloat162float(__float2bfloat16_rn(y));
+        e2 = __fmaf_rn(r, r, e2);
+      }
+      atomicMax(maxnorm2_bits, __float_as_uint(n2 * 1.00002f + 1e-30f));
+      atomicMax(maxnorm2_bits + 1, __float_as_uint(e2 * 1.00002f + 1e-30f));
+    }
   }
   __syncthreads();
   if (out_f32) {
@@ -83,37 +93,56 @@ int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode,
 
 // Query staging: bf16 copy (zero padded to [nq_pad, d_pad]), filter slack, selection state reset.
 // One warp per query row.
+//
+// EXACT-mode slack.  Let s be the fixed-order fp32 score of (q, x) and b the tensor-core score of the bf16
+// copies (q^, x^).  q.x - q^.x^ = q.(x - x^) + (q - q^).x^, so
+//     |s - b| <= ||q|| * max_rows ||x - x^||  +  ||q - q^|| * max_rows ||x^||  +  accumulation slack,
+// with the two maxima measured exactly when rows are added (stats[1], stats[0]) and the query terms measured
+// here; the accumulation slack covers d fp32 roundings on our side and a generous 8x that inside the tensor
+// core.  This is a rigorous bound, about 2.3x tighter than 2^-7 * ||q|| * ||x||.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad, int d, int d_pad,
-                                    __nv_bfloat16* __restrict__ q_bf16, float eps, const unsigned int* maxnorm2_bits,
+                                    __nv_bfloat16* __restrict__ q_bf16, int exact, const unsigned int* stats,
                                     SelectState st) {
   const int warps_per_block = blockDim.x / 32;
   const int64_t row = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= nq_pad) return;
-  float ss = 0.0f;
+  float ss = 0.0f, ee = 0.0f;
   for (int j = lane; j < d_pad; j += 32) {
     float v = (row < nq && j < d) ? q[row * (int64_t)d + j] : 0.0f;
+    const __nv_bfloat16 vb = __float2bfloat16_rn(v);
+    const float r = v - __bfloat162float(vb);
     ss += v * v;
-    if (q_bf16) q_bf16[row * (int64_t)d_pad + j] = __float2bfloat16_rn(v);
+    ee += r * r;
+    if (q_bf16) q_bf16[row * (int64_t)d_pad + j] = vb;
   }
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    ee += __shfl_xor_sync(0xffffffffu, ee, o);
+  }
   if (lane == 0) {
-    float mx = maxnorm2_bits ? __uint_as_float(*maxnorm2_bits) : 0.0f;
-    // |exact - tensor-core score| <= eps * ||q|| * max||x|| (Cauchy-Schwarz on the bf16 input rounding)
-    st.margin[row] = eps > 0.0f ? eps * sqrtf(ss * 1.00002f) * sqrtf(mx) + 1e-30f : 0.0f;
+    float m = 0.0f;
+    if (exact && stats != nullptr) {
+      const float xn = sqrtf(__uint_as_float(stats[0]));   // max ||x||   (inflated at add time)
+      const float xe = sqrtf(__uint_as_float(stats[1]));   // max ||x - x^||
+      const float qn = sqrtf(ss * 1.0001f), qe = sqrtf(ee * 1.0001f);
+      m = (qn * xe + qe * (xn + xe)) * 1.0001f + (float)d * 5.4e-7f * qn * xn + 1e-30f;
+    }
+    st.margin[row] = m;
     st.thr[row] = row < nq ? -INFINITY : INFINITY;
     st.cnt[row] = 0;
     st.nret[row] = 0;
+    st.done[row] = 0;
     if (row == 0) *st.overflow = 0;
   }
 }
 
-int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, float eps,
-                        const unsigned int* maxnorm2_bits, SelectState st, cudaStream_t stream) {
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
+                        const unsigned int* stats, SelectState st, cudaStream_t stream) {
   const int wpb = 8;
   int64_t blocks = (nq_pad + wpb - 1) / wpb;
   prep_queries_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(q, nq, nq_pad, d, d_pad, (__nv_bfloat16*)q_bf16,
-                                                                  eps, maxnorm2_bits, st);
+                                                                  exact, stats, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

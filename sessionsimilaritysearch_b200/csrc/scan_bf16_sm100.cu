@@ -14,9 +14,10 @@
 //   warps 4-11      two epilogue warpgroups (slots 0/2 and 1/3).  A thread owns ONE query (TMEM lane):
 //                   tcgen05.ld 32 columns -> 3-input max tree -> one compare against the query's running
 //                   threshold.  Only when some lane of the warp sees max > thr does the warp take the slow
-//                   path: those lanes dump their 32 raw scores as a 144-byte HitRecord into the warp's
-//                   private record region (slot index from a ballot — no atomics).  expand/refine
-//                   (select.cu) turn records into exact top-k lists and tighter thresholds between waves.
+//                   path: those lanes dump their 32 raw scores as a 144-byte HitRecord into the private
+//                   sub-region of (their query, this CTA, their warpgroup) — a register counter, no atomics.
+//                   refine (select.cu) turns a query's records into exact top-k lists and a tighter
+//                   threshold between waves.
 //
 // Arithmetic intensity: a CTA holding num_mt*128 resident queries does 2*num_mt*128*128*d_pad flop per
 // 128*d_pad*2 bytes of DB tile, i.e. num_mt*128 flop/byte — 512 flop/B at num_mt=4, well above the B200
@@ -253,11 +254,11 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int ew = warp - 4;
     const int wg = ew >> 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
-    const uint32_t region = (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (uint32_t)ew;
-    HitRecord* myrec = p.rec + (size_t)region * p.rec_cap;
-    uint32_t wcount = 0;
+    // this thread's queries: m-tile mt -> query (mt_base + mt) * 128 + quarter * 32 + lane; one record counter each
+    uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+    const uint32_t sub_stride = gridDim.x * 2u;                          // sub-regions per query
+    const uint32_t my_sub = blockIdx.x * 2u + (uint32_t)wg;
     const int total_units = my_tiles * num_mt;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     // unit u = (tile iteration it, resident m-tile mt); this warpgroup takes u = wg, wg+2, ...
     int it = 0, mt = wg;
     while (mt >= num_mt) { mt -= num_mt; ++it; }
@@ -265,9 +266,11 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t slot = (uint32_t)(u & 3);
       const uint32_t ph = (uint32_t)((u >> 2) & 1);
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int cur_mt = mt;
       const uint32_t qidx = (uint32_t)((mt_base + mt) * kTileQ + quarter * 32 + lane);
       const float thr = p.st.thr[qidx];
       const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * kTileRows);
+      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * kRecSubCap;
       mt += 2;
       while (mt >= num_mt) { mt -= num_mt; ++it; }
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 105);
@@ -295,22 +298,25 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
         const float mx = fmaxf(max3(m0, m1, m2), m3);
         const bool hit = mx > thr;
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (bal != 0u) {
+        if (__any_sync(0xffffffffu, hit)) {
           if (hit) {
-            const uint32_t idx = wcount + __popc(bal & lt_mask);
-            if (idx < (uint32_t)p.rec_cap) {
+            const uint32_t idx = cur_mt == 0 ? rc0 : cur_mt == 1 ? rc1 : cur_mt == 2 ? rc2 : rc3;
+            if (idx < (uint32_t)kRecSubCap) {
               uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
               dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
 #pragma unroll
               for (int i = 0; i < 8; ++i) dst[1 + i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
             }
+            rc0 += cur_mt == 0; rc1 += cur_mt == 1; rc2 += cur_mt == 2; rc3 += cur_mt == 3;
           }
-          wcount += __popc(bal);
         }
       }
     }
-    if (lane == 0) p.rec_cnt[region] = wcount;
+    // publish (and thereby reset) the record count of every sub-region this thread owns
+    for (int m = 0; m < num_mt; ++m) {
+      const uint32_t qidx = (uint32_t)((mt_base + m) * kTileQ + quarter * 32 + lane);
+      p.rec_cnt[(size_t)qidx * sub_stride + my_sub] = m == 0 ? rc0 : m == 1 ? rc1 : m == 2 ? rc2 : rc3;
+    }
   }
 
   tc_fence_before();
@@ -372,8 +378,8 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
   SSS_REQUIRE(stages >= 2, "not enough shared memory for the DB tile ring");
   plan->num_stages = stages;
   plan->smem_bytes = 1024 + q_bytes + stages * stage_bytes + kBarrierBytes;
-  plan->rec_cap = 1024;
-  plan->n_regions = plan->grid_x * plan->grid_y * 8;
+  plan->rec_cap = kRecSubCap;
+  plan->n_regions = (int)nq_pad * plan->grid_x * 2;
   return 0;
 }
 

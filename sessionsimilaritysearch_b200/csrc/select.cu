@@ -13,115 +13,21 @@
 
 namespace sss {
 
-// ---- expand: tensor-core hit records -> per-query candidate lists -----------------------------------
-__global__ void __launch_bounds__(128) expand_records_kernel(const HitRecord* __restrict__ rec,
-                                                             const uint32_t* __restrict__ rec_cnt, int rec_cap,
-                                                             int64_t row_limit, SelectState st) {
-  const int region = blockIdx.x;
-  uint32_t n = rec_cnt[region];
-  if (n > (uint32_t)rec_cap) {
-    if (threadIdx.x == 0) *st.overflow = 1;
-    n = rec_cap;
-  }
-  // 4 threads per record: each takes 8 of the 32 scores (two float4 loads)
-  const int sub = threadIdx.x & 3;
-  for (uint32_t e = threadIdx.x >> 2; e < n; e += blockDim.x >> 2) {
-    const HitRecord* r = rec + (size_t)region * rec_cap + e;
-    const uint32_t q = r->q;
-    const uint32_t row_base = r->row_base + sub * 8;
-    const float thr = st.thr[q];
-    const float4* v4 = reinterpret_cast<const float4*>(r->v) + sub * 2;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float4 v = v4[c];
-      float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int64_t row = (int64_t)row_base + c * 4 + t;
-        if (vv[t] > thr && row < row_limit) {
-          uint32_t slot = atomicAdd(&st.cnt[q], 1u);
-          if (slot < (uint32_t)st.cap) st.cand[(size_t)q * st.cap + slot] = pack_cand(score_key(vv[t]), (uint32_t)row);
-        }
-      }
-    }
-  }
-}
-
-int launch_expand_records(const HitRecord* rec, const uint32_t* rec_cnt, int n_regions, int rec_cap, int64_t row_limit,
-                          SelectState st, cudaStream_t stream) {
-  expand_records_kernel<<<n_regions, 128, 0, stream>>>(rec, rec_cnt, rec_cap, row_limit, st);
-  SSS_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// ---- rescore: exact fixed-order fp32 score of every NEW candidate (EXACT mode) ------------------------
-// One block per query, 8 warps.  A warp takes 32 new candidates at a time: their rows are read with fully
-// coalesced 128-byte requests (one row segment per request, lane = column) into a warp-private shared tile,
-// then lane l walks ITS row in k-ascending order with a single accumulator — the same rounding sequence as
-// the fp32 scan and the oracle — and rewrites the candidate's key in place.
-constexpr int RS_WARPS = 8;
-constexpr int RS_KC = 32;  // columns staged per round
-__global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(RefineArgs a, SelectState st) {
-  extern __shared__ float rs_smem[];
-  float* qs = rs_smem;                                    // [d_round] the query
-  const int d_round = (a.d + RS_KC - 1) / RS_KC * RS_KC;
-  float* tiles = rs_smem + d_round;                       // [RS_WARPS][32][RS_KC + 1]
-  const int q = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t c = st.cnt[q];
-  const int n = c > (uint32_t)st.cap ? st.cap : (int)c;
-  const int nr = (int)st.nret[q];
-  if (n <= nr) return;
-  for (int j = threadIdx.x; j < d_round; j += blockDim.x) qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
-  __syncthreads();
-  uint64_t* g = st.cand + (size_t)q * st.cap;
-  float* tile = tiles + (size_t)warp * 32 * (RS_KC + 1);
-  for (int base = nr + warp * 32; base < n; base += RS_WARPS * 32) {
-    const int i = base + lane;
-    const uint64_t v = i < n ? g[i] : 0ull;
-    const uint32_t my_row = i < n ? cand_id(v) : 0u;
-    float acc = 0.0f;
-    for (int k0 = 0; k0 < a.d; k0 += RS_KC) {
-      const int col = k0 + lane;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
-        tile[r * (RS_KC + 1) + lane] = col < a.d ? a.db_f32[(size_t)row * a.d + col] : 0.0f;
-      }
-      __syncwarp();
-      const float* mine = tile + lane * (RS_KC + 1);
-      if (a.metric == 0) {
-#pragma unroll
-        for (int kk = 0; kk < RS_KC; ++kk) acc = __fmaf_rn(qs[k0 + kk], mine[kk], acc);
-      } else {
-#pragma unroll
-        for (int kk = 0; kk < RS_KC; ++kk) {
-          // padded columns: q = x = 0 -> t = 0 -> acc unchanged
-          const float t = __fsub_rn(qs[k0 + kk], mine[kk]);
-          acc = __fmaf_rn(t, t, acc);
-        }
-      }
-      __syncwarp();
-    }
-    if (i < n) g[i] = pack_cand(score_key(a.metric == 0 ? acc : -acc), my_row);
-  }
-}
-
-int launch_rescore(const RefineArgs& a, SelectState st, cudaStream_t stream) {
-  const int d_round = (a.d + RS_KC - 1) / RS_KC * RS_KC;
-  size_t smem = sizeof(float) * ((size_t)d_round + (size_t)RS_WARPS * 32 * (RS_KC + 1));
-  SSS_REQUIRE(smem <= 96 * 1024, "embedding width too large for rescore_kernel");
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  rescore_kernel<<<(unsigned)a.nq, RS_WARPS * 32, smem, stream>>>(a, st);
-  SSS_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// ---- refine -----------------------------------------------------------------------------------------
+// ---- refine ------------------------------------------------------------------------------------------
+// One block per query.  Input: the retained entries [0, nret) of the query's list (final keys, ids as
+// returned) plus the NEW row-level candidates of the last scan wave, which arrive either
+//   * as list entries [nret, cnt) appended with atomics by the fp32 / Hamming scans, or
+//   * as tensor-core hit records in the query's private sub-regions (a.rec != nullptr): each record holds 32
+//     raw scores, re-filtered here against the same threshold the scan used.
+// Steps:
+//   1. group by session with a shared-memory hash table (owner = session, best = max key);
+//   2. EXACT mode only: a new row whose tensor-core score is more than 2*margin below its session's best
+//      cannot hold the session's exact maximum (|exact - bf16| <= margin), so only the others survive and are
+//      re-scored: rows are fetched with coalesced 16-byte loads into a warp-private tile, then lane l walks ITS
+//      row in k-ascending order with one accumulator — the rounding sequence of the fp32 scan and the oracle;
+//   3. per-session max of the final keys, compaction, bitonic sort, keep the best k, raise the threshold.
+// Two instantiations run back to back every wave: a small one (most queries, several blocks per SM) and a
+// large one that picks up the queries the small one had to skip (done[q] != wave).
 __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   for (int k2 = 2; k2 <= P; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
@@ -141,76 +47,257 @@ __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   }
 }
 
-__global__ void __launch_bounds__(256) refine_kernel(RefineArgs a, SelectState st) {
-  extern __shared__ uint64_t e[];
-  __shared__ int s_m;
+template <int NE, int SLOT_BITS, int RSW, int KC, int THREADS, int RMAX, bool LAST>
+struct RefineCfg {
+  static constexpr int kNE = NE;               // max entries (retained + new) per query and wave
+  static constexpr int kSlots = 1 << SLOT_BITS;
+  static constexpr int kRsw = RSW;             // re-scoring warps
+  static constexpr int kKc = KC;               // tile columns
+  static constexpr int kThreads = THREADS;
+  static constexpr int kRmax = RMAX;           // max hit records per query and wave
+  static constexpr bool kLast = LAST;          // nobody behind us: too-large inputs are an overflow
+  static constexpr int kMaxSub = 512;          // max record sub-regions per query (2 * grid_x)
+  static constexpr size_t smem_bytes(int d_round, bool rescore) {
+    return (size_t)NE * 8 + (size_t)kSlots * 8 + (size_t)NE * 2 + (size_t)NE * 2 + (size_t)RMAX * 4 +
+           (size_t)(kMaxSub + 1) * 4 + sizeof(float) * ((size_t)RSW * 32 * (KC + 1) + (rescore ? d_round : 0));
+  }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::kThreads) refine_kernel(RefineArgs a, SelectState st) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  uint64_t* ent = reinterpret_cast<uint64_t*>(rf_smem);                      // [NE]
+  uint32_t* owner = reinterpret_cast<uint32_t*>(ent + C::kNE);               // [slots] session + 1
+  uint32_t* best = owner + C::kSlots;                                        // [slots] max key
+  uint16_t* slot = reinterpret_cast<uint16_t*>(best + C::kSlots);            // [NE]
+  uint16_t* list = slot + C::kNE;                                            // [NE] survivors
+  uint32_t* recptr = reinterpret_cast<uint32_t*>(list + C::kNE);             // [RMAX] global record index
+  uint32_t* subpre = recptr + C::kRmax;                                      // [kMaxSub + 1] prefix of record counts
+  float* tiles = reinterpret_cast<float*>(subpre + C::kMaxSub + 1);          // [RSW][32][KC+1]
+  float* qs = tiles + C::kRsw * 32 * (C::kKc + 1);                           // [d_round]
+  __shared__ int s_n, s_nsurv, s_H, s_skip;
+
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int cap = st.cap;
-  const uint32_t c = st.cnt[q];
-  const int n = c > (uint32_t)cap ? cap : (int)c;
-  if (c > (uint32_t)cap && tid == 0) *st.overflow = 1;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (st.done[q] == a.wave) return;  // the small instantiation already handled this query
   const int nr = (int)st.nret[q];
-  if (n == nr) return;  // nothing new since the last refine
+  uint64_t* g = st.cand + (size_t)q * st.cap;
+  const float margin = st.margin[q];
+  const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
+  int n;
+
+  if (tid == 0) {
+    s_nsurv = 0;
+    s_H = 0;
+    s_skip = 0;
+    s_n = nr;
+  }
+  for (int h = tid; h < C::kSlots; h += C::kThreads) {
+    owner[h] = 0u;
+    best[h] = 0u;
+  }
+  if (a.rec != nullptr) {
+    // ---- new candidates from hit records
+    const int nsub = a.rec_nsub;
+    const size_t sub0 = (size_t)q * nsub;
+    if (tid == 0) subpre[0] = 0u;
+    __syncthreads();
+    // counts -> exclusive prefix (nsub <= 512: one pass by warp 0 over chunks of 32)
+    if (warp == 0) {
+      uint32_t run = 0;
+      for (int s0 = 0; s0 < nsub; s0 += 32) {
+        uint32_t cnt = 0;
+        if (s0 + lane < nsub) {
+          cnt = a.rec_cnt[sub0 + s0 + lane];
+          if (cnt > (uint32_t)kRecSubCap) {
+            *st.overflow = 1;
+            cnt = kRecSubCap;
+          }
+        }
+        uint32_t inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (s0 + lane < nsub) subpre[s0 + lane + 1] = run + inc;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    const int R = (int)subpre[nsub];
+    if (R == 0) return;  // nothing new since the last refine
+    if (R > C::kRmax) {
+      if (!C::kLast) return;  // leave it to the large instantiation
+      if (tid == 0) *st.overflow = 1;
+    }
+    const int Rc = R < C::kRmax ? R : C::kRmax;
+    for (int s = tid; s < nsub; s += C::kThreads) {
+      const uint32_t b0 = subpre[s], b1 = subpre[s + 1];
+      for (uint32_t j = b0; j < b1 && j < (uint32_t)C::kRmax; ++j)
+        recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
+    }
+    for (int i = tid; i < nr; i += C::kThreads) ent[i] = g[i];
+    __syncthreads();
+    const float thr = st.thr[q];
+    for (int t = tid; t < Rc * 32; t += C::kThreads) {
+      const HitRecord* r = a.rec + recptr[t >> 5];
+      const float v = r->v[t & 31];
+      const int64_t row = (int64_t)r->row_base + (t & 31);
+      if (v > thr && row < a.row_limit) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < C::kNE) ent[pos] = pack_cand(score_key(v), (uint32_t)row);
+      }
+    }
+    __syncthreads();
+    n = s_n;
+    if (n > C::kNE) {
+      if (!C::kLast) return;
+      if (tid == 0) *st.overflow = 1;
+      n = C::kNE;
+    }
+  } else {
+    // ---- new candidates from the list
+    const uint32_t c = st.cnt[q];
+    n = c > (uint32_t)st.cap ? st.cap : (int)c;
+    if (c > (uint32_t)st.cap && tid == 0) *st.overflow = 1;
+    if (n == nr) return;  // nothing new since the last refine
+    if (n > C::kNE) {
+      if (!C::kLast) return;
+      if (tid == 0) *st.overflow = 1;
+      n = C::kNE;
+    }
+    for (int i = tid; i < n; i += C::kThreads) ent[i] = g[i];
+  }
+  if (a.rescore)
+    for (int j = tid; j < d_round; j += C::kThreads) qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
+  __syncthreads();
+
+  // 1. group by session
+  for (int i = tid; i < n; i += C::kThreads) {
+    const uint64_t v = ent[i];
+    const uint32_t id = cand_id(v);
+    const uint32_t sess = (i < nr || !a.reduce_max) ? id : (uint32_t)a.row_seg[id];
+    uint32_t h = (sess * 2654435761u) >> (32 - (C::kSlots == 4096 ? 12 : 11));
+    for (int probe = 0; probe < C::kSlots; ++probe) {
+      const uint32_t prev = atomicCAS(&owner[h], 0u, sess + 1u);
+      if (prev == 0u || prev == sess + 1u) break;
+      h = (h + 1u) & (C::kSlots - 1);
+    }
+    atomicMax(&best[h], cand_key(v));
+    slot[i] = (uint16_t)h;
+  }
+  __syncthreads();
+
+  if (a.rescore) {
+    // 2a. survivors among the new rows
+    for (int i = nr + tid; i < n; i += C::kThreads) {
+      const float b = key_score(cand_key(ent[i]));
+      const float lo = key_score(best[slot[i]]) - 2.0f * margin;
+      if (b >= lo) list[atomicAdd(&s_nsurv, 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+    // final keys only from here on: retained entries keep theirs, survivors get exact ones
+    for (int h = tid; h < C::kSlots; h += C::kThreads) best[h] = 0u;
+    __syncthreads();
+    for (int i = tid; i < nr; i += C::kThreads) atomicMax(&best[slot[i]], cand_key(ent[i]));
+    // 2b. exact fixed-order re-scoring of the survivors
+    const int nsurv = s_nsurv;
+    if (warp < C::kRsw) {
+      constexpr int LPR = C::kKc / 4;   // lanes per row segment (float4 each)
+      constexpr int RPI = 32 / LPR;     // rows per load instruction
+      float* tile = tiles + (size_t)warp * 32 * (C::kKc + 1);
+      const int rsub = lane / LPR, c4 = lane % LPR;
+      for (int base = warp * 32; base < nsurv; base += C::kRsw * 32) {
+        const int li = base + lane;
+        const int i = li < nsurv ? (int)list[li] : -1;
+        const uint32_t my_row = i >= 0 ? cand_id(ent[i]) : 0u;
+        float acc = 0.0f;
+        for (int k0 = 0; k0 < a.d; k0 += C::kKc) {
+          const int col = k0 + c4 * 4;
+#pragma unroll
+          for (int t = 0; t < 32 / RPI; ++t) {
+            const int r = t * RPI + rsub;
+            const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+            const float* src = a.db_f32 + (size_t)row * a.d + col;
+            float4 v;
+            if (col + 3 < a.d && (a.d & 3) == 0) {
+              v = *reinterpret_cast<const float4*>(src);
+            } else {
+              v.x = col + 0 < a.d ? src[0] : 0.0f;
+              v.y = col + 1 < a.d ? src[1] : 0.0f;
+              v.z = col + 2 < a.d ? src[2] : 0.0f;
+              v.w = col + 3 < a.d ? src[3] : 0.0f;
+            }
+            float* dst = tile + r * (C::kKc + 1) + c4 * 4;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          }
+          __syncwarp();
+          const float* mine = tile + lane * (C::kKc + 1);
+          if (a.metric == 0) {
+#pragma unroll
+            for (int kk = 0; kk < C::kKc; ++kk) acc = __fmaf_rn(qs[k0 + kk], mine[kk], acc);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < C::kKc; ++kk) {
+              const float t = __fsub_rn(qs[k0 + kk], mine[kk]);  // padded columns: 0 - 0
+              acc = __fmaf_rn(t, t, acc);
+            }
+          }
+          __syncwarp();
+        }
+        if (i >= 0) atomicMax(&best[slot[i]], score_key(a.metric == 0 ? acc : -acc));
+      }
+    }
+    __syncthreads();
+  }
+
+  // 3. one entry per session, best k of them
+  for (int h = tid; h < C::kSlots; h += C::kThreads) {
+    const uint32_t o = owner[h];
+    if (o != 0u && best[h] != 0u) ent[atomicAdd(&s_H, 1)] = pack_cand(best[h], o - 1u);
+  }
+  __syncthreads();
+  const int H = s_H;
   int P = 2;
-  while (P < n) P <<= 1;
-  uint64_t* g = st.cand + (size_t)q * cap;
-  for (int i = tid; i < P; i += blockDim.x) {
-    uint64_t v = i < n ? g[i] : 0ull;
-    if (a.reduce_max && i >= nr && i < n) v = pack_cand(cand_key(v), (uint32_t)a.row_seg[cand_id(v)]);
-    e[i] = v;
-  }
-  if (tid == 0) s_m = 0;
+  while (P < H) P <<= 1;
+  for (int i = H + tid; i < P; i += C::kThreads) ent[i] = 0ull;
   __syncthreads();
-  if (a.reduce_max) {
-    // session-major order: (~id) in the high word, key in the low word; descending sort groups a
-    // session's entries with its best score first.
-    for (int i = tid; i < P; i += blockDim.x) {
-      uint64_t v = e[i];
-      e[i] = v ? ((v << 32) | (v >> 32)) : 0ull;
-    }
-    __syncthreads();
-    bitonic_desc(e, P);
-    uint32_t headmask = 0;  // P <= 8192, 256 threads -> at most 32 entries per thread
-    int t = 0;
-    for (int i = tid; i < P; i += blockDim.x, ++t) {
-      uint64_t v = e[i];
-      bool head = v != 0ull && (i == 0 || (uint32_t)(e[i - 1] >> 32) != (uint32_t)(v >> 32));
-      headmask |= (head ? 1u : 0u) << t;
-    }
-    __syncthreads();
-    t = 0;
-    for (int i = tid; i < P; i += blockDim.x, ++t) {
-      uint64_t v = e[i];
-      e[i] = ((headmask >> t) & 1u) ? ((v << 32) | (v >> 32)) : 0ull;
-    }
-    __syncthreads();
-  }
-  bitonic_desc(e, P);
-  for (int i = tid; i < P; i += blockDim.x)
-    if (e[i] != 0ull && (i == P - 1 || e[i + 1] == 0ull)) s_m = i + 1;
-  __syncthreads();
-  const int m = s_m < a.k ? s_m : a.k;
-  for (int i = tid; i < m; i += blockDim.x) g[i] = e[i];
+  bitonic_desc(ent, P);
+  const int m = H < a.k ? H : a.k;
+  for (int i = tid; i < m; i += C::kThreads) g[i] = ent[i];
   if (tid == 0) {
     st.cnt[q] = m;
     st.nret[q] = m;
-    st.thr[q] = m == a.k ? key_score(cand_key(e[a.k - 1])) - st.margin[q] : -INFINITY;
+    st.thr[q] = m == a.k ? key_score(cand_key(ent[a.k - 1])) - margin : -INFINITY;
+    st.done[q] = a.wave;
   }
 }
 
-int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream) {
-  if (a.rescore && launch_rescore(a, st, stream)) return 1;
-  size_t smem = (size_t)st.cap * sizeof(uint64_t);
-  SSS_REQUIRE(st.cap <= 8192, "candidate capacity too large for refine_kernel");
-  static bool attr_done = false;
-  if (!attr_done) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    attr_done = true;
+using RefineSmall = RefineCfg<2048, 11, 4, 16, 256, 512, false>;
+using RefineLarge = RefineCfg<4096, 12, 6, 32, 512, 4096, true>;
+
+template <class C>
+static int launch_refine_cfg(const RefineArgs& a, SelectState st, cudaStream_t stream, size_t* smem_set) {
+  const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
+  const size_t smem = C::smem_bytes(d_round, a.rescore != 0);
+  SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine_kernel");
+  if (smem > *smem_set) {
+    SSS_CUDA_OK(cudaFuncSetAttribute(refine_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *smem_set = smem;
   }
-  refine_kernel<<<(unsigned)a.nq, 256, smem, stream>>>(a, st);
+  refine_kernel<C><<<(unsigned)a.nq, C::kThreads, smem, stream>>>(a, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream) {
+  SSS_REQUIRE(st.cap <= RefineLarge::kNE, "candidate capacity too large for refine_kernel");
+  SSS_REQUIRE(a.k <= RefineLarge::kNE / 2, "k too large for refine_kernel");
+  SSS_REQUIRE(a.rec == nullptr || a.rec_nsub <= RefineLarge::kMaxSub, "too many record sub-regions per query");
+  static size_t smem_small = 0, smem_large = 0;
+  if (a.k <= RefineSmall::kNE / 4 && launch_refine_cfg<RefineSmall>(a, st, stream, &smem_small)) return 1;
+  return launch_refine_cfg<RefineLarge>(a, st, stream, &smem_large);
 }
 
 // ---- emit -------------------------------------------------------------------------------------------
