@@ -45,7 +45,7 @@ struct Workspace {
   int64_t nq_pad = 0;
   int cap = 0, d = 0, d_pad = 0, k = 0;
   float *thr = nullptr, *margin = nullptr, *q_f32 = nullptr, *out_D = nullptr;
-  uint32_t *cnt = nullptr, *nret = nullptr, *done = nullptr;
+  uint32_t *cnt = nullptr, *nret = nullptr, *skip_list = nullptr, *skip_cnt = nullptr;
   uint64_t* cand = nullptr;
   int* flags = nullptr;  // [0] overflow, [1] kernel watchdog
   void* q_bf16 = nullptr;
@@ -64,7 +64,7 @@ struct Workspace {
       d = d_;
       d_pad = d_pad_;
       if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&cnt, nq_pad) ||
-          dev_alloc(&nret, nq_pad) || dev_alloc(&done, nq_pad) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
+          dev_alloc(&nret, nq_pad) || dev_alloc(&skip_list, nq_pad) || dev_alloc(&skip_cnt, 2) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
         return 1;
       void* v = nullptr;
       SSS_CUDA_OK(cudaMalloc(&v, (size_t)nq_pad * d_pad * 2));
@@ -94,7 +94,7 @@ struct Workspace {
     return 0;
   }
   void release_query_side() {
-    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(done); dev_free(cand); dev_free(q_f32);
+    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(skip_list); dev_free(skip_cnt); dev_free(cand); dev_free(q_f32);
     if (q_bf16) cudaFree(q_bf16);
     q_bf16 = nullptr;
   }
@@ -105,7 +105,8 @@ struct Workspace {
   }
   SelectState state() const {
     SelectState s;
-    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.done = done; s.overflow = flags;
+    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.skip_list = skip_list; s.skip_cnt = skip_cnt;
+    s.overflow = flags;
     s.cap = cap;
     return s;
   }
@@ -311,6 +312,9 @@ static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe
   std::vector<int64_t> ends;
   int64_t first = std::max<int64_t>(128, (std::min<int64_t>(cap / 2, cap - k) / 128) * 128);
   if (first > 2048) first = 2048;
+  // without session grouping every row is its own group: a shorter threshold-less first wave keeps the
+  // common case inside the small refine instantiation (<= 768 groups)
+  if (!safe && !dense_groups && k <= 256) first = 512;
   int64_t e = std::min(n_rows, first);
   ends.push_back(e);
   while (e < n_rows) {
@@ -415,8 +419,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
         ix->stat_kernels += 1;
       }
-      if (launch_refine(ra, state, st)) return 1;
-      ix->stat_kernels += b.k <= 512 ? 2 : 1;
+      if (launch_refine(ra, state, ix->num_sms, st)) return 1;
+      ix->stat_kernels += b.k <= 256 ? 2 : 1;
       ix->stat_waves += 1;
       begin = end;
     }
@@ -663,7 +667,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
       if (rc) break;
       ra.wave += 1;
       rc = launch_scan_hamming(ix->codes, ix->pitch, begin, end, ix->q_codes, nq, state, st);
-      if (!rc) rc = launch_refine(ra, state, st);
+      if (!rc) rc = launch_refine(ra, state, 148, st);
       begin = end;
     }
     if (!rc) rc = launch_emit_hamming(state, nq, k, ix->nbits, ix->id_offset, Ddev, Idev, st);

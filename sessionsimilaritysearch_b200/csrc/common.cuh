@@ -61,7 +61,8 @@ struct SelectState {
   uint32_t* nret;    // [nq_pad] entries [0, nret) are retained (already reduced) from earlier waves
   uint64_t* cand;    // [nq_pad, cap]
   float* margin;     // [nq_pad] filter slack of the bf16 scan in EXACT mode, else 0
-  uint32_t* done;    // [nq_pad] id of the last wave whose refine has processed this query
+  uint32_t* skip_list;  // [nq_pad] queries the small refine left to the large one (this wave)
+  uint32_t* skip_cnt;   // [2] length of skip_list, indexed by wave parity
   int* overflow;     // [1] set when any list / record region overflowed
   int cap;
 };

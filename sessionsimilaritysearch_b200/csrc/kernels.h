@@ -51,14 +51,15 @@ struct RefineArgs {
   const float* q_f32;        // [nq, d] when rescore
   int d;
   int metric;
-  uint32_t wave;             // id of this wave (st.done bookkeeping), > 0
+  uint32_t wave;             // id of this wave (skip-list parity), > 0
+  int all_large;             // set by launch_refine: k too large for the small instantiation
   const HitRecord* rec;      // tensor-core hit records of this wave, or nullptr for list input
   const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
   int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
   int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill
 };
 // group by session, (EXACT) prune + re-score survivors, keep the best k, raise the threshold
-int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream);
+int launch_refine(const RefineArgs& a, SelectState st, int num_sms, cudaStream_t stream);
 int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
                 cudaStream_t stream);
 int launch_topk_merge(const float* cD, const int64_t* cI, int n_shards, int64_t nq, int k, int metric, float* D,

@@ -132,8 +132,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int
     st.thr[row] = row < nq ? -INFINITY : INFINITY;
     st.cnt[row] = 0;
     st.nret[row] = 0;
-    st.done[row] = 0;
-    if (row == 0) *st.overflow = 0;
+    if (row == 0) {
+      *st.overflow = 0;
+      st.skip_cnt[0] = 0;
+      st.skip_cnt[1] = 0;
+    }
   }
 }
 

@@ -276,16 +276,8 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 105);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (uint32_t)kTileRows;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (c == 3) {  // accumulators are in registers: hand the TMEM slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
-        }
+      // Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c goes through the max tree.
+      auto process = [&](const uint32_t (&r)[32], int c) {
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
@@ -310,7 +302,24 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             rc0 += cur_mt == 0; rc1 += cur_mt == 1; rc2 += cur_mt == 2; rc3 += cur_mt == 3;
           }
         }
-      }
+      };
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 32u, rb);
+      process(ra, 0);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 64u, ra);
+      process(rb, 1);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 96u, rb);
+      process(ra, 2);
+      tmem_ld_wait();
+      // all four chunks have left TMEM: hand the slot back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+      process(rb, 3);
     }
     // publish (and thereby reset) the record count of every sub-region this thread owns
     for (int m = 0; m < num_mt; ++m) {

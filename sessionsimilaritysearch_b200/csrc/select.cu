@@ -8,26 +8,28 @@
 // Replaces the heap/reservoir inside faiss' IndexFlat*.search (test_amazon_filterd.py:578) [recalled].
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sss {
 
 // ---- refine ------------------------------------------------------------------------------------------
-// One block per query.  Input: the retained entries [0, nret) of the query's list (final keys, ids as
-// returned) plus the NEW row-level candidates of the last scan wave, which arrive either
+// Per query and wave.  Input: the retained entries [0, nret) of the query's list (final keys, ids as returned)
+// plus the NEW row-level candidates of the last scan wave, which arrive either
 //   * as list entries [nret, cnt) appended with atomics by the fp32 / Hamming scans, or
 //   * as tensor-core hit records in the query's private sub-regions (a.rec != nullptr): each record holds 32
-//     raw scores, re-filtered here against the same threshold the scan used.
-// Steps:
-//   1. group by session with a shared-memory hash table (owner = session, best = max key);
-//   2. EXACT mode only: a new row whose tensor-core score is more than 2*margin below its session's best
-//      cannot hold the session's exact maximum (|exact - bf16| <= margin), so only the others survive and are
+//     raw scores, re-filtered here against the threshold the scan used.
+// Steps (all in shared memory, candidates are streamed, never materialised):
+//   1. pass 1 groups candidates by session in a hash table (owner = session, best = max key);
+//   2. EXACT mode only: pass 2 keeps a new row only if its tensor-core score is within 2*margin of its session's
+//      best (|exact - bf16| <= margin, so the others cannot hold the session's exact maximum); the survivors are
 //      re-scored: rows are fetched with coalesced 16-byte loads into a warp-private tile, then lane l walks ITS
 //      row in k-ascending order with one accumulator — the rounding sequence of the fp32 scan and the oracle;
 //   3. per-session max of the final keys, compaction, bitonic sort, keep the best k, raise the threshold.
-// Two instantiations run back to back every wave: a small one (most queries, several blocks per SM) and a
-// large one that picks up the queries the small one had to skip (done[q] != wave).
+// A small instantiation (one block per query, ~35 KB, 6 blocks per SM) serves the common case; queries it cannot
+// hold go on a skip list that a large instantiation (persistent, one block per SM) drains right after.
 __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   for (int k2 = 2; k2 <= P; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
@@ -47,64 +49,162 @@ __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   }
 }
 
-template <int NE, int SLOT_BITS, int RSW, int KC, int THREADS, int RMAX, bool LAST>
+template <int SLOT_BITS, int SURV, int KMAX, int RSW, int KC, int THREADS, int RMAX, bool LAST>
 struct RefineCfg {
-  static constexpr int kNE = NE;               // max entries (retained + new) per query and wave
-  static constexpr int kSlots = 1 << SLOT_BITS;
-  static constexpr int kRsw = RSW;             // re-scoring warps
-  static constexpr int kKc = KC;               // tile columns
+  static constexpr int kSlotBits = SLOT_BITS;
+  static constexpr int kSlots = 1 << SLOT_BITS;  // hash slots = max distinct sessions per query and wave
+  static constexpr int kSurv = SURV;             // max rows re-scored per query and wave
+  static constexpr int kKmax = KMAX;             // max k (retained entries)
+  static constexpr int kRsw = RSW;               // re-scoring warps
+  static constexpr int kKc = KC;                 // tile columns
   static constexpr int kThreads = THREADS;
-  static constexpr int kRmax = RMAX;           // max hit records per query and wave
-  static constexpr bool kLast = LAST;          // nobody behind us: too-large inputs are an overflow
-  static constexpr int kMaxSub = 512;          // max record sub-regions per query (2 * grid_x)
+  static constexpr int kRmax = RMAX;             // max hit records per query and wave
+  static constexpr bool kLast = LAST;            // nobody behind us: too-large inputs are an overflow
+  static constexpr int kMaxSub = 512;            // max record sub-regions per query (2 * grid_x)
+  // scratch = [recptr | subpre | tiles], reused as the gather/sort array A[kSlots] once the passes are done
+  __host__ __device__ static constexpr size_t scratch_bytes() {
+    size_t s = (size_t)RMAX * 4 + (size_t)(kMaxSub + 1) * 4 + 4 + sizeof(float) * (size_t)RSW * 32 * (KC + 1);
+    size_t a = (size_t)kSlots * 8;
+    return (s > a ? s : a) + 8;
+  }
   static constexpr size_t smem_bytes(int d_round, bool rescore) {
-    return (size_t)NE * 8 + (size_t)kSlots * 8 + (size_t)NE * 2 + (size_t)NE * 2 + (size_t)RMAX * 4 +
-           (size_t)(kMaxSub + 1) * 4 + sizeof(float) * ((size_t)RSW * 32 * (KC + 1) + (rescore ? d_round : 0));
+    return scratch_bytes() + (size_t)kSlots * 8 + (size_t)SURV * 4 + 16 + (size_t)SURV * 2 + (size_t)KMAX * 2 + 8 +
+           sizeof(float) * (rescore ? d_round : 0);
   }
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::kThreads) refine_kernel(RefineArgs a, SelectState st) {
-  extern __shared__ __align__(16) unsigned char rf_smem[];
-  uint64_t* ent = reinterpret_cast<uint64_t*>(rf_smem);                      // [NE]
-  uint32_t* owner = reinterpret_cast<uint32_t*>(ent + C::kNE);               // [slots] session + 1
-  uint32_t* best = owner + C::kSlots;                                        // [slots] max key
-  uint16_t* slot = reinterpret_cast<uint16_t*>(best + C::kSlots);            // [NE]
-  uint16_t* list = slot + C::kNE;                                            // [NE] survivors
-  uint32_t* recptr = reinterpret_cast<uint32_t*>(list + C::kNE);             // [RMAX] global record index
-  uint32_t* subpre = recptr + C::kRmax;                                      // [kMaxSub + 1] prefix of record counts
-  float* tiles = reinterpret_cast<float*>(subpre + C::kMaxSub + 1);          // [RSW][32][KC+1]
-  float* qs = tiles + C::kRsw * 32 * (C::kKc + 1);                           // [d_round]
-  __shared__ int s_n, s_nsurv, s_H, s_skip;
+enum { RF_DONE = 0, RF_SKIP = 1 };
 
-  const int q = blockIdx.x;
+template <class C>
+struct RefineSmem {
+  uint64_t* A;          // [slots] gather + sort
+  uint32_t* owner;      // [slots] session + 1
+  uint32_t* best;       // [slots] max key
+  uint32_t* surv_row;   // [SURV]
+  uint32_t* recptr;     // [RMAX] global record index
+  uint32_t* subpre;     // [kMaxSub + 1]
+  int* ctr;             // [4] s_nsurv, s_H, s_uniq, s_fail
+  uint16_t* surv_slot;  // [SURV]
+  uint16_t* ret_slot;   // [KMAX]
+  float* tiles;         // [RSW][32][KC+1]
+  float* qs;            // [d_round]
+  __device__ explicit RefineSmem(unsigned char* p) {
+    // scratch first (8-byte aligned): A overlays recptr/subpre/tiles
+    A = reinterpret_cast<uint64_t*>(p);
+    recptr = reinterpret_cast<uint32_t*>(p);
+    subpre = recptr + C::kRmax;
+    tiles = reinterpret_cast<float*>(subpre + C::kMaxSub + 2);
+    unsigned char* rest = p + C::scratch_bytes();
+    owner = reinterpret_cast<uint32_t*>(rest);
+    best = owner + C::kSlots;
+    surv_row = best + C::kSlots;
+    ctr = reinterpret_cast<int*>(surv_row + C::kSurv);
+    surv_slot = reinterpret_cast<uint16_t*>(ctr + 4);
+    ret_slot = surv_slot + C::kSurv;
+    qs = reinterpret_cast<float*>(ret_slot + C::kKmax + ((C::kSurv + C::kKmax) & 1));
+  }
+};
+
+// claim-or-find the slot of `sess`; -1 when the table is full
+template <class C>
+__device__ __forceinline__ int rf_insert(const RefineSmem<C>& sm, uint32_t sess) {
+  uint32_t h = (sess * 2654435761u) >> (32 - C::kSlotBits);
+  for (int probe = 0; probe < C::kSlots; ++probe) {
+    const uint32_t prev = atomicCAS(&sm.owner[h], 0u, sess + 1u);
+    if (prev == 0u) {
+      atomicAdd(&sm.ctr[2], 1);
+      return (int)h;
+    }
+    if (prev == sess + 1u) return (int)h;
+    h = (h + 1u) & (C::kSlots - 1);
+  }
+  sm.ctr[3] = 1;
+  return -1;
+}
+template <class C>
+__device__ __forceinline__ int rf_find(const RefineSmem<C>& sm, uint32_t sess) {
+  uint32_t h = (sess * 2654435761u) >> (32 - C::kSlotBits);
+  for (int probe = 0; probe < C::kSlots; ++probe) {
+    const uint32_t o = sm.owner[h];
+    if (o == sess + 1u) return (int)h;
+    if (o == 0u) return -1;
+    h = (h + 1u) & (C::kSlots - 1);
+  }
+  return -1;
+}
+
+// stream the new candidates of query q through f(key, row, session); four independent loads (and session
+// gathers) are in flight per thread, consecutive threads read consecutive scores of a record
+template <class C, class F>
+__device__ __forceinline__ void rf_for_each(const RefineArgs& a, const SelectState& st, const RefineSmem<C>& sm,
+                                            const uint64_t* g, int nr, int n, int Rc, float thr, F f) {
+  constexpr int U = 4;
+  if (a.rec != nullptr) {
+    const int total = Rc * 32;
+    for (int t0 = threadIdx.x; t0 < total; t0 += U * C::kThreads) {
+      float v[U];
+      uint32_t row[U], sess[U];
+      bool pass[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * C::kThreads;
+        pass[u] = t < total;
+        const HitRecord* r = a.rec + sm.recptr[pass[u] ? (t >> 5) : 0];
+        v[u] = r->v[t & 31];
+        row[u] = r->row_base + (uint32_t)(t & 31);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pass[u] = pass[u] && v[u] > thr && (int64_t)row[u] < a.row_limit;
+        sess[u] = (pass[u] && a.reduce_max) ? (uint32_t)a.row_seg[row[u]] : row[u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pass[u]) f(score_key(v[u]), row[u], sess[u]);
+    }
+  } else {
+    for (int i0 = nr + threadIdx.x; i0 < n; i0 += U * C::kThreads) {
+      uint64_t e[U];
+      uint32_t sess[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * C::kThreads;
+        e[u] = i < n ? g[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        sess[u] = (e[u] != 0ull && a.reduce_max) ? (uint32_t)a.row_seg[cand_id(e[u])] : cand_id(e[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (e[u] != 0ull) f(cand_key(e[u]), cand_id(e[u]), sess[u]);
+    }
+  }
+}
+
+template <class C>
+__device__ int refine_query(const RefineArgs& a, const SelectState& st, const RefineSmem<C>& sm, int q) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  if (st.done[q] == a.wave) return;  // the small instantiation already handled this query
   const int nr = (int)st.nret[q];
   uint64_t* g = st.cand + (size_t)q * st.cap;
   const float margin = st.margin[q];
+  const float thr = st.thr[q];
   const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
-  int n;
+  int n = nr, Rc = 0;
 
-  if (tid == 0) {
-    s_nsurv = 0;
-    s_H = 0;
-    s_skip = 0;
-    s_n = nr;
-  }
+  __syncthreads();  // previous query of a persistent block is fully done with shared memory
   for (int h = tid; h < C::kSlots; h += C::kThreads) {
-    owner[h] = 0u;
-    best[h] = 0u;
+    sm.owner[h] = 0u;
+    sm.best[h] = 0u;
   }
+  if (tid < 4) sm.ctr[tid] = 0;
+  if (tid == 0) sm.subpre[0] = 0u;
+  __syncthreads();
+
   if (a.rec != nullptr) {
-    // ---- new candidates from hit records
     const int nsub = a.rec_nsub;
     const size_t sub0 = (size_t)q * nsub;
-    if (tid == 0) subpre[0] = 0u;
-    __syncthreads();
-    // counts -> exclusive prefix (nsub <= 512: one pass by warp 0 over chunks of 32)
-    if (warp == 0) {
+    if (warp == 0) {  // record counts of the query's sub-regions -> exclusive prefix
       uint32_t run = 0;
       for (int s0 = 0; s0 < nsub; s0 += 32) {
         uint32_t cnt = 0;
@@ -120,184 +220,221 @@ __global__ void __launch_bounds__(C::kThreads) refine_kernel(RefineArgs a, Selec
           uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += t;
         }
-        if (s0 + lane < nsub) subpre[s0 + lane + 1] = run + inc;
+        if (s0 + lane < nsub) sm.subpre[s0 + lane + 1] = run + inc;
         run += __shfl_sync(0xffffffffu, inc, 31);
       }
     }
     __syncthreads();
-    const int R = (int)subpre[nsub];
-    if (R == 0) return;  // nothing new since the last refine
+    const int R = (int)sm.subpre[nsub];
+    if (R == 0) return RF_DONE;  // nothing new since the last refine
     if (R > C::kRmax) {
-      if (!C::kLast) return;  // leave it to the large instantiation
+      if (!C::kLast) return RF_SKIP;
       if (tid == 0) *st.overflow = 1;
     }
-    const int Rc = R < C::kRmax ? R : C::kRmax;
+    Rc = R < C::kRmax ? R : C::kRmax;
     for (int s = tid; s < nsub; s += C::kThreads) {
-      const uint32_t b0 = subpre[s], b1 = subpre[s + 1];
+      const uint32_t b0 = sm.subpre[s], b1 = sm.subpre[s + 1];
       for (uint32_t j = b0; j < b1 && j < (uint32_t)C::kRmax; ++j)
-        recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
-    }
-    for (int i = tid; i < nr; i += C::kThreads) ent[i] = g[i];
-    __syncthreads();
-    const float thr = st.thr[q];
-    for (int t = tid; t < Rc * 32; t += C::kThreads) {
-      const HitRecord* r = a.rec + recptr[t >> 5];
-      const float v = r->v[t & 31];
-      const int64_t row = (int64_t)r->row_base + (t & 31);
-      if (v > thr && row < a.row_limit) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < C::kNE) ent[pos] = pack_cand(score_key(v), (uint32_t)row);
-      }
-    }
-    __syncthreads();
-    n = s_n;
-    if (n > C::kNE) {
-      if (!C::kLast) return;
-      if (tid == 0) *st.overflow = 1;
-      n = C::kNE;
+        sm.recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
     }
   } else {
-    // ---- new candidates from the list
     const uint32_t c = st.cnt[q];
     n = c > (uint32_t)st.cap ? st.cap : (int)c;
     if (c > (uint32_t)st.cap && tid == 0) *st.overflow = 1;
-    if (n == nr) return;  // nothing new since the last refine
-    if (n > C::kNE) {
-      if (!C::kLast) return;
-      if (tid == 0) *st.overflow = 1;
-      n = C::kNE;
-    }
-    for (int i = tid; i < n; i += C::kThreads) ent[i] = g[i];
+    if (n == nr) return RF_DONE;  // nothing new since the last refine
   }
   if (a.rescore)
-    for (int j = tid; j < d_round; j += C::kThreads) qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
-  __syncthreads();
-
-  // 1. group by session
-  for (int i = tid; i < n; i += C::kThreads) {
-    const uint64_t v = ent[i];
-    const uint32_t id = cand_id(v);
-    const uint32_t sess = (i < nr || !a.reduce_max) ? id : (uint32_t)a.row_seg[id];
-    uint32_t h = (sess * 2654435761u) >> (32 - (C::kSlots == 4096 ? 12 : 11));
-    for (int probe = 0; probe < C::kSlots; ++probe) {
-      const uint32_t prev = atomicCAS(&owner[h], 0u, sess + 1u);
-      if (prev == 0u || prev == sess + 1u) break;
-      h = (h + 1u) & (C::kSlots - 1);
-    }
-    atomicMax(&best[h], cand_key(v));
-    slot[i] = (uint16_t)h;
+    for (int j = tid; j < d_round; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
+  // retained entries first: they own their slots and keep their (final) keys
+  for (int i = tid; i < nr; i += C::kThreads) {
+    const uint64_t e = g[i];
+    const int h = rf_insert<C>(sm, cand_id(e));
+    if (h >= 0) atomicMax(&sm.best[h], cand_key(e));
+    sm.ret_slot[i] = (uint16_t)(h >= 0 ? h : 0);
   }
   __syncthreads();
+
+  // 1. group the new candidates by session
+  rf_for_each<C>(a, st, sm, g, nr, n, Rc, thr, [&](uint32_t key, uint32_t row, uint32_t sess) {
+    const int h = rf_insert<C>(sm, sess);
+    if (h >= 0) atomicMax(&sm.best[h], key);
+  });
+  __syncthreads();
+  if (sm.ctr[3] != 0 || sm.ctr[2] > C::kSlots * 3 / 4) {
+    if (!C::kLast) return RF_SKIP;
+    if (sm.ctr[3] != 0 && tid == 0) *st.overflow = 1;  // table full: candidates were dropped
+  }
 
   if (a.rescore) {
     // 2a. survivors among the new rows
-    for (int i = nr + tid; i < n; i += C::kThreads) {
-      const float b = key_score(cand_key(ent[i]));
-      const float lo = key_score(best[slot[i]]) - 2.0f * margin;
-      if (b >= lo) list[atomicAdd(&s_nsurv, 1)] = (uint16_t)i;
+    rf_for_each<C>(a, st, sm, g, nr, n, Rc, thr, [&](uint32_t key, uint32_t row, uint32_t sess) {
+      const int h = rf_find<C>(sm, sess);
+      if (h < 0) return;
+      if (key_score(key) >= key_score(sm.best[h]) - 2.0f * margin) {
+        const int pos = atomicAdd(&sm.ctr[0], 1);
+        if (pos < C::kSurv) {
+          sm.surv_row[pos] = row;
+          sm.surv_slot[pos] = (uint16_t)h;
+        }
+      }
+    });
+    __syncthreads();
+    int nsurv = sm.ctr[0];
+    if (nsurv > C::kSurv) {
+      if (!C::kLast) return RF_SKIP;
+      if (tid == 0) *st.overflow = 1;
+      nsurv = C::kSurv;
     }
-    __syncthreads();
     // final keys only from here on: retained entries keep theirs, survivors get exact ones
-    for (int h = tid; h < C::kSlots; h += C::kThreads) best[h] = 0u;
+    for (int h = tid; h < C::kSlots; h += C::kThreads) sm.best[h] = 0u;
     __syncthreads();
-    for (int i = tid; i < nr; i += C::kThreads) atomicMax(&best[slot[i]], cand_key(ent[i]));
+    for (int i = tid; i < nr; i += C::kThreads) atomicMax(&sm.best[sm.ret_slot[i]], cand_key(g[i]));
     // 2b. exact fixed-order re-scoring of the survivors
-    const int nsurv = s_nsurv;
     if (warp < C::kRsw) {
       constexpr int LPR = C::kKc / 4;   // lanes per row segment (float4 each)
       constexpr int RPI = 32 / LPR;     // rows per load instruction
-      float* tile = tiles + (size_t)warp * 32 * (C::kKc + 1);
+      float* tile = sm.tiles + (size_t)warp * 32 * (C::kKc + 1);
       const int rsub = lane / LPR, c4 = lane % LPR;
+      constexpr int NL = 32 / RPI;      // load instructions per tile
+      const bool vec_ok = (a.d & 3) == 0;
       for (int base = warp * 32; base < nsurv; base += C::kRsw * 32) {
         const int li = base + lane;
-        const int i = li < nsurv ? (int)list[li] : -1;
-        const uint32_t my_row = i >= 0 ? cand_id(ent[i]) : 0u;
-        float acc = 0.0f;
-        for (int k0 = 0; k0 < a.d; k0 += C::kKc) {
+        const bool live = li < nsurv;
+        const uint32_t my_row = live ? sm.surv_row[li] : 0u;
+        const float* rowp[NL];
+#pragma unroll
+        for (int t = 0; t < NL; ++t)
+          rowp[t] = a.db_f32 + (size_t)__shfl_sync(0xffffffffu, my_row, t * RPI + rsub) * a.d;
+        auto load_tile = [&](int k0, float4 (&v)[NL]) {
           const int col = k0 + c4 * 4;
 #pragma unroll
-          for (int t = 0; t < 32 / RPI; ++t) {
-            const int r = t * RPI + rsub;
-            const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
-            const float* src = a.db_f32 + (size_t)row * a.d + col;
-            float4 v;
-            if (col + 3 < a.d && (a.d & 3) == 0) {
-              v = *reinterpret_cast<const float4*>(src);
+          for (int t = 0; t < NL; ++t) {
+            const float* src = rowp[t] + col;
+            if (vec_ok && col + 3 < a.d) {
+              v[t] = *reinterpret_cast<const float4*>(src);
             } else {
-              v.x = col + 0 < a.d ? src[0] : 0.0f;
-              v.y = col + 1 < a.d ? src[1] : 0.0f;
-              v.z = col + 2 < a.d ? src[2] : 0.0f;
-              v.w = col + 3 < a.d ? src[3] : 0.0f;
+              v[t].x = col + 0 < a.d ? src[0] : 0.0f;
+              v[t].y = col + 1 < a.d ? src[1] : 0.0f;
+              v[t].z = col + 2 < a.d ? src[2] : 0.0f;
+              v[t].w = col + 3 < a.d ? src[3] : 0.0f;
             }
-            float* dst = tile + r * (C::kKc + 1) + c4 * 4;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          }
+        };
+        float4 cur[NL], nxt[NL];
+        load_tile(0, cur);
+        float acc = 0.0f;
+        for (int k0 = 0; k0 < a.d; k0 += C::kKc) {
+          const bool more = k0 + C::kKc < a.d;
+          if (more) load_tile(k0 + C::kKc, nxt);
+#pragma unroll
+          for (int t = 0; t < NL; ++t) {
+            float* dst = tile + (t * RPI + rsub) * (C::kKc + 1) + c4 * 4;
+            dst[0] = cur[t].x; dst[1] = cur[t].y; dst[2] = cur[t].z; dst[3] = cur[t].w;
           }
           __syncwarp();
           const float* mine = tile + lane * (C::kKc + 1);
           if (a.metric == 0) {
 #pragma unroll
-            for (int kk = 0; kk < C::kKc; ++kk) acc = __fmaf_rn(qs[k0 + kk], mine[kk], acc);
+            for (int kk = 0; kk < C::kKc; ++kk) acc = __fmaf_rn(sm.qs[k0 + kk], mine[kk], acc);
           } else {
 #pragma unroll
             for (int kk = 0; kk < C::kKc; ++kk) {
-              const float t = __fsub_rn(qs[k0 + kk], mine[kk]);  // padded columns: 0 - 0
+              const float t = __fsub_rn(sm.qs[k0 + kk], mine[kk]);  // padded columns: 0 - 0
               acc = __fmaf_rn(t, t, acc);
             }
           }
           __syncwarp();
+          if (more) {
+#pragma unroll
+            for (int t = 0; t < NL; ++t) cur[t] = nxt[t];
+          }
         }
-        if (i >= 0) atomicMax(&best[slot[i]], score_key(a.metric == 0 ? acc : -acc));
+        if (live) atomicMax(&sm.best[sm.surv_slot[li]], score_key(a.metric == 0 ? acc : -acc));
       }
     }
     __syncthreads();
   }
 
-  // 3. one entry per session, best k of them
+  // 3. one entry per session, best k of them (A overlays the record scratch: every pass is finished)
+  __syncthreads();
   for (int h = tid; h < C::kSlots; h += C::kThreads) {
-    const uint32_t o = owner[h];
-    if (o != 0u && best[h] != 0u) ent[atomicAdd(&s_H, 1)] = pack_cand(best[h], o - 1u);
+    const uint32_t o = sm.owner[h];
+    if (o != 0u && sm.best[h] != 0u) sm.A[atomicAdd(&sm.ctr[1], 1)] = pack_cand(sm.best[h], o - 1u);
   }
   __syncthreads();
-  const int H = s_H;
+  const int H = sm.ctr[1];
   int P = 2;
   while (P < H) P <<= 1;
-  for (int i = H + tid; i < P; i += C::kThreads) ent[i] = 0ull;
+  for (int i = H + tid; i < P; i += C::kThreads) sm.A[i] = 0ull;
   __syncthreads();
-  bitonic_desc(ent, P);
+  bitonic_desc(sm.A, P);
   const int m = H < a.k ? H : a.k;
-  for (int i = tid; i < m; i += C::kThreads) g[i] = ent[i];
+  for (int i = tid; i < m; i += C::kThreads) g[i] = sm.A[i];
   if (tid == 0) {
     st.cnt[q] = m;
     st.nret[q] = m;
-    st.thr[q] = m == a.k ? key_score(cand_key(ent[a.k - 1])) - margin : -INFINITY;
-    st.done[q] = a.wave;
+    st.thr[q] = m == a.k ? key_score(cand_key(sm.A[a.k - 1])) - margin : -INFINITY;
   }
+  return RF_DONE;
 }
 
-using RefineSmall = RefineCfg<2048, 11, 4, 16, 256, 512, false>;
-using RefineLarge = RefineCfg<4096, 12, 6, 32, 512, 4096, true>;
-
+// one block per query; queries that do not fit go on the skip list of this wave
 template <class C>
-static int launch_refine_cfg(const RefineArgs& a, SelectState st, cudaStream_t stream, size_t* smem_set) {
-  const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
-  const size_t smem = C::smem_bytes(d_round, a.rescore != 0);
-  SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine_kernel");
-  if (smem > *smem_set) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(refine_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    *smem_set = smem;
-  }
-  refine_kernel<C><<<(unsigned)a.nq, C::kThreads, smem, stream>>>(a, st);
-  SSS_CUDA_OK(cudaGetLastError());
-  return 0;
+__global__ void __launch_bounds__(C::kThreads) refine_small_kernel(RefineArgs a, SelectState st) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  RefineSmem<C> sm(rf_smem);
+  const int q = blockIdx.x;
+  if (refine_query<C>(a, st, sm, q) == RF_SKIP && threadIdx.x == 0)
+    st.skip_list[atomicAdd(&st.skip_cnt[a.wave & 1u], 1u)] = (uint32_t)q;
 }
 
-int launch_refine(const RefineArgs& a, SelectState st, cudaStream_t stream) {
-  SSS_REQUIRE(st.cap <= RefineLarge::kNE, "candidate capacity too large for refine_kernel");
-  SSS_REQUIRE(a.k <= RefineLarge::kNE / 2, "k too large for refine_kernel");
+// persistent: drains the skip list (or every query when a.all_large)
+template <class C>
+__global__ void __launch_bounds__(C::kThreads) refine_large_kernel(RefineArgs a, SelectState st) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  RefineSmem<C> sm(rf_smem);
+  const uint32_t count = a.all_large ? (uint32_t)a.nq : st.skip_cnt[a.wave & 1u];
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.skip_cnt[(a.wave + 1u) & 1u] = 0u;  // for the next wave
+  for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+    const int q = a.all_large ? (int)i : (int)st.skip_list[i];
+    refine_query<C>(a, st, sm, q);
+  }
+}
+
+using RefineSmall = RefineCfg<10, 1024, 512, 4, 16, 256, 512, false>;
+using RefineLarge = RefineCfg<12, 4096, 2048, 6, 32, 512, 4096, true>;
+
+int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStream_t stream) {
+  RefineArgs a = a_in;
+  SSS_REQUIRE(st.cap <= RefineLarge::kSlots, "candidate capacity too large for refine");
+  SSS_REQUIRE(a.k <= RefineLarge::kKmax, "k too large for refine");
   SSS_REQUIRE(a.rec == nullptr || a.rec_nsub <= RefineLarge::kMaxSub, "too many record sub-regions per query");
   static size_t smem_small = 0, smem_large = 0;
-  if (a.k <= RefineSmall::kNE / 4 && launch_refine_cfg<RefineSmall>(a, st, stream, &smem_small)) return 1;
-  return launch_refine_cfg<RefineLarge>(a, st, stream, &smem_large);
+  a.all_large = a.k > RefineSmall::kKmax / 2 ? 1 : 0;
+  if (!a.all_large) {
+    const int d_round = (a.d + RefineSmall::kKc - 1) / RefineSmall::kKc * RefineSmall::kKc;
+    const size_t smem = RefineSmall::smem_bytes(d_round, a.rescore != 0);
+    SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
+    if (smem > smem_small) {
+      SSS_CUDA_OK(cudaFuncSetAttribute(refine_small_kernel<RefineSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      smem_small = smem;
+    }
+    refine_small_kernel<RefineSmall><<<(unsigned)a.nq, RefineSmall::kThreads, smem, stream>>>(a, st);
+    SSS_CUDA_OK(cudaGetLastError());
+  }
+  const int d_round = (a.d + RefineLarge::kKc - 1) / RefineLarge::kKc * RefineLarge::kKc;
+  const size_t smem = RefineLarge::smem_bytes(d_round, a.rescore != 0);
+  SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
+  if (smem > smem_large) {
+    SSS_CUDA_OK(cudaFuncSetAttribute(refine_large_kernel<RefineLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    smem_large = smem;
+  }
+  int grid = (int)std::min<int64_t>(a.nq, num_sms);
+  refine_large_kernel<RefineLarge><<<grid, RefineLarge::kThreads, smem, stream>>>(a, st);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // ---- emit -------------------------------------------------------------------------------------------
