@@ -411,7 +411,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.rec_nsub = tensor ? plan.grid_x * 2 : 0;
       ra.row_limit = n_rows;
       if (wave_tensor) {
-        if (launch_scan_bf16(plan, tmap_q, tmap_db, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st)) return 1;
+        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st))
+          return 1;
         if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
         ix->stat_kernels += 1;
       } else {

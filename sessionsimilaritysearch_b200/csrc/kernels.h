@@ -31,14 +31,15 @@ struct Bf16ScanPlan {
   int grid_y;       // CTA groups along the queries
   int smem_bytes;
   int rec_cap;      // hit records per epilogue warp
-  int n_regions;    // grid_x * grid_y * 8 epilogue warps
+  int n_regions;    // record sub-regions: nq_pad * grid_x * 2
+  bool ts;          // query tiles resident in TMEM (A operand from TMEM) instead of shared memory
 };
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
-int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, int64_t row_begin,
-                     int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt, int* err_flag,
-                     cudaStream_t stream);
+int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
+                     int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
+                     int* err_flag, cudaStream_t stream);
 
 // select.cu
 struct RefineArgs {

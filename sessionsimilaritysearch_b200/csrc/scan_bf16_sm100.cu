@@ -25,6 +25,7 @@
 // stream) below.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -110,6 +111,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (lane = query row, one 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -144,6 +167,7 @@ struct ScanParams {
   uint32_t* rec_cnt;
   int rec_cap;
   int* err_flag;
+  const uint4* q_bf16;   // [nq_pad, d_pad] bf16, 16-byte aligned rows (TS variant reads it directly)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -336,6 +360,211 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TS variant: the resident query tiles live in TENSOR MEMORY (A operand from TMEM), so shared memory carries
+// only the DB ring (7 stages at d=128) and a tcgen05.mma reads 4 KB instead of 8 KB of shared memory per K=16
+// step — at N=128 the SS form sits exactly on the 128 B/cycle shared-memory port and the tensor pipe stalls.
+// TMEM: [0, a_cols) = A (num_mt * num_kb * 32 columns: lane = query, column = two bf16), then two 128-column
+// accumulator slots (slot == epilogue warpgroup).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNumThreads, 1)
+scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int mt_base = blockIdx.y * p.num_mt;
+  const int num_mt = min(p.num_mt, p.total_mtiles - mt_base);
+  const int n_tiles = (int)p.n_tiles;
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  const uint32_t db_smem = smem_base;
+  const uint32_t bar_base = db_smem + (uint32_t)(p.num_stages * p.num_kb) * kKBlockBytes;
+  const uint32_t full_bar = bar_base;                         // [kMaxStages]
+  const uint32_t empty_bar = bar_base + 8 * kMaxStages;       // [kMaxStages]
+  const uint32_t tfull_bar = bar_base + 16 * kMaxStages;      // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                 // [2]
+  const uint32_t qready_bar = tempty_bar + 16;                // [1]
+  const uint32_t tmem_ptr_addr = qready_bar + 8;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_db);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp of the owning warpgroup
+    }
+    mbar_init(qready_bar, 8);            // every epilogue warp has stored its share of Q
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+  const uint32_t a_cols = (uint32_t)(p.num_mt * p.num_kb) * 32u;
+  const uint32_t d_base = tmem_base + a_cols;
+
+  if (warp == 0) {
+    // ===================== TMA producer: DB tiles only =====================
+    if (lane == 0 && my_tiles > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 201);
+        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.num_kb * kKBlockBytes);
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int row = (int)p.row_begin + tile * kTileRows;
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes, &tmap_db, full_bar + 8 * stage,
+                      kb * 64, row);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(qready_bar, 0, p.err_flag, 202);
+      tc_fence_after();
+      uint32_t u = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 203);
+        tc_fence_after();
+        for (int mt = 0; mt < num_mt; ++mt, ++u) {
+          const uint32_t slot = u & 1u;
+          mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 204);
+          tc_fence_after();
+          const uint32_t d_tmem = d_base + slot * (uint32_t)kTileRows;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const uint32_t a_tmem = tmem_base + (uint32_t)(mt * p.num_kb + kb) * 32u;
+            const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)  // K=16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
+              umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(tfull_bar + 8 * slot);
+        }
+        umma_commit(empty_bar + 8 * stage);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 4;
+    const int wg = ew >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    // ---- stage this warp's share of the query tiles into TMEM (warpgroup wg takes m-tiles wg, wg+2)
+    if (my_tiles > 0) {
+      const int row_words = p.num_kb * 8;  // uint4 per query row
+      for (int mt = wg; mt < num_mt; mt += 2) {
+        const uint4* src = p.q_bf16 + (size_t)((mt_base + mt) * kTileQ + quarter * 32 + lane) * row_words;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          uint32_t w[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = src[kb * 8 + i];
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+          }
+          tmem_st32(tmem_base + lane_base + (uint32_t)(mt * p.num_kb + kb) * 32u, w);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qready_bar);
+    }
+    // ---- fused top-k filter
+    uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+    const uint32_t sub_stride = gridDim.x * 2u;
+    const uint32_t my_sub = blockIdx.x * 2u + (uint32_t)wg;
+    const int total_units = my_tiles * num_mt;
+    int it = 0, mt = wg;
+    while (mt >= num_mt) { mt -= num_mt; ++it; }
+    for (int u = wg; u < total_units; u += 2) {
+      const uint32_t slot = (uint32_t)wg;  // u & 1
+      const uint32_t ph = (uint32_t)((u >> 1) & 1);
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int cur_mt = mt;
+      const uint32_t qidx = (uint32_t)((mt_base + mt) * kTileQ + quarter * 32 + lane);
+      const float thr = p.st.thr[qidx];
+      const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * kTileRows);
+      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * kRecSubCap;
+      mt += 2;
+      while (mt >= num_mt) { mt -= num_mt; ++it; }
+      mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 205);
+      tc_fence_after();
+      const uint32_t taddr = d_base + lane_base + slot * (uint32_t)kTileRows;
+      auto process = [&](const uint32_t (&r)[32], int c) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+        float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]);
+        float m2 = max3(f[6], f[7], f[8]), m3 = max3(f[9], f[10], f[11]);
+        m0 = max3(m0, f[12], f[13]); m1 = max3(m1, f[14], f[15]);
+        m2 = max3(m2, f[16], f[17]); m3 = max3(m3, f[18], f[19]);
+        m0 = max3(m0, f[20], f[21]); m1 = max3(m1, f[22], f[23]);
+        m2 = max3(m2, f[24], f[25]); m3 = max3(m3, f[26], f[27]);
+        m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
+        const float mx = fmaxf(max3(m0, m1, m2), m3);
+        const bool hit = mx > thr;
+        if (__any_sync(0xffffffffu, hit)) {
+          if (hit) {
+            const uint32_t idx = cur_mt == 0 ? rc0 : cur_mt == 1 ? rc1 : cur_mt == 2 ? rc2 : rc3;
+            if (idx < (uint32_t)kRecSubCap) {
+              uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
+              dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[1 + i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+            rc0 += cur_mt == 0; rc1 += cur_mt == 1; rc2 += cur_mt == 2; rc3 += cur_mt == 3;
+          }
+        }
+      };
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 32u, rb);
+      process(ra, 0);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 64u, ra);
+      process(rb, 1);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 96u, rb);
+      process(ra, 2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+      process(rb, 3);
+    }
+    for (int m = 0; m < num_mt; ++m) {
+      const uint32_t qidx = (uint32_t)((mt_base + m) * kTileQ + quarter * 32 + lane);
+      p.rec_cnt[(size_t)qidx * sub_stride + my_sub] = m == 0 ? rc0 : m == 1 ? rc1 : m == 2 ? rc2 : rc3;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -379,7 +608,9 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
   plan->num_mt = (total_mtiles + plan->grid_y - 1) / plan->grid_y;
   plan->grid_x = num_sms / plan->grid_y;
   if (plan->grid_x < 1) plan->grid_x = 1;
-  const int q_bytes = plan->num_mt * plan->num_kb * kKBlockBytes;
+  const char* force_ss = getenv("SSS_SCAN_SS");
+  plan->ts = !(force_ss && force_ss[0] == '1');  // A operand from TMEM unless the SS form is forced
+  const int q_bytes = plan->ts ? 0 : plan->num_mt * plan->num_kb * kKBlockBytes;
   const int stage_bytes = plan->num_kb * kKBlockBytes;
   const int avail = 227 * 1024 - 1024 - kBarrierBytes - q_bytes;
   int stages = avail / stage_bytes;
@@ -392,9 +623,9 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
   return 0;
 }
 
-int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, int64_t row_begin,
-                     int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt, int* err_flag,
-                     cudaStream_t stream) {
+int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
+                     int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
+                     int* err_flag, cudaStream_t stream) {
   SSS_REQUIRE(row_begin % kTileRows == 0, "scan wave must start on a 128-row boundary");
   ScanParams p;
   p.num_kb = plan.num_kb;
@@ -408,15 +639,21 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.rec_cnt = rec_cnt;
   p.rec_cap = plan.rec_cap;
   p.err_flag = err_flag;
+  p.q_bf16 = (const uint4*)q_bf16;
   if (p.n_tiles <= 0) return 0;
   static int smem_set = 0;
   if (smem_set < plan.smem_bytes) {
     SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     plan.smem_bytes));
     smem_set = plan.smem_bytes;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  scan_bf16_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_q,
-                                                                   *(const CUtensorMap*)tmap_db, p);
+  if (plan.ts)
+    scan_bf16_ts_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_db, p);
+  else
+    scan_bf16_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_q,
+                                                                     *(const CUtensorMap*)tmap_db, p);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
