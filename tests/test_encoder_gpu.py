@@ -1,0 +1,98 @@
+"""GPU parity tests of the encoder path (sss_encoder_forward, sss_binarize_head, sss_item_vote) against the CPU
+oracle and the goldens produced by the reference's own model code."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import encoder_common as ec  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", ec.CONFIGS, ids=[c[0] for c in ec.CONFIGS])
+def test_encoder_matches_reference_golden_and_oracle(cfg):
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from sessionsimilaritysearch_b200 import graph, sessions
+    name, in_dim, hidden, n_layers, out_dim, msl, n_sess, seed = cfg
+    gold = np.load(os.path.join(HERE, "golden", "encoder_golden_%s.npz" % name))
+    _, graphs = ec.make_graphs(n_sess, in_dim, seed, sessions.sequence_to_graph)
+    data = graph.collate(graphs)
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, seed)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    out = enc(data.to("cuda")).cpu().numpy()
+    scale = float(np.abs(gold["out"]).max())
+    # fp32 GEMM summation order differs between cuBLAS and the CPU: tolerance 2e-4 of the output scale
+    np.testing.assert_allclose(out, gold["out"], rtol=2e-4, atol=2e-4 * scale)
+    ref = eo.encoder_forward(P, eo.batch_from_pyg(graph.collate(graphs)), n_layers).numpy()
+    np.testing.assert_allclose(out, ref, rtol=2e-4, atol=2e-4 * scale)
+    # deterministic run to run
+    assert np.array_equal(out, enc(data).cpu().numpy())
+    # hash head on the golden embeddings reproduces the reference's codes exactly where |pre-activation| is not ~0
+    head = sss.BinarizeHead(torch.from_numpy(gold["head_w"]), torch.from_numpy(gold["head_b"]))
+    codes = head(torch.from_numpy(gold["out"])).cpu().numpy()
+    pre = gold["out"] @ gold["head_w"].T + gold["head_b"]
+    safe = np.abs(pre) > 1e-4 * np.abs(pre).max()
+    assert np.array_equal(codes[safe], gold["codes"][safe]) and set(np.unique(codes)) <= {-1.0, 0.0, 1.0}
+
+
+def test_encoder_larger_batch_against_oracle():
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from sessionsimilaritysearch_b200 import graph, sessions
+    in_dim, hidden, n_layers, out_dim, msl = 48, 64, 3, 100, 20
+    _, graphs = ec.make_graphs(200, in_dim, 3, sessions.sequence_to_graph)     # the reference's eval batch size
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 3)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    loader = graph.DataLoader(graphs, batch_size=200, shuffle=False)
+    data = next(iter(loader))
+    out = enc(data.to("cuda")).cpu().numpy()
+    ref = eo.encoder_forward(P, eo.batch_from_pyg(graph.collate(graphs)), n_layers).numpy()
+    np.testing.assert_allclose(out, ref, rtol=3e-4, atol=3e-4 * float(np.abs(ref).max()))
+    assert out.shape == (200, out_dim)
+
+
+def test_nan_input_raises_like_the_reference():
+    import sessionsimilaritysearch_b200 as sss
+    from sessionsimilaritysearch_b200 import graph, sessions
+    in_dim, hidden, n_layers, out_dim, msl = 24, 32, 3, 60, 20
+    _, graphs = ec.make_graphs(4, in_dim, 7, sessions.sequence_to_graph)
+    graphs[2]['query'].x[0, 3] = float("nan")
+    enc = sss.SessionEncoder(ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 7), in_dim=in_dim, hidden=hidden,
+                             n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    with pytest.raises(RuntimeError):
+        enc(graph.collate(graphs).to("cuda"))
+
+
+def test_item_vote_and_get_prediction_by_knn(oracle):
+    import sessionsimilaritysearch_b200 as sss
+    rng = np.random.default_rng(14)
+    n_sess = 400
+    lens = rng.integers(1, 9, size=n_sess)
+    item_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    items = rng.integers(0, 300, size=item_off[-1]).astype(np.int64)
+    lists = sss.ItemLists([items[item_off[i]:item_off[i + 1]] for i in range(n_sess)])
+    I = np.stack([rng.permutation(n_sess)[:60] for _ in range(9)]).astype(np.int64)
+    I[0, 50:] = -1                       # padded neighbours are skipped
+    D = np.sort(rng.random((9, 60)).astype(np.float32), axis=1)[:, ::-1].copy()
+    oi, ow = sss.item_vote(D, I, lists, 20)
+    ei, ew = oracle.item_vote(D, I, item_off, items, 20)
+    assert np.array_equal(oi.cpu().numpy(), ei)
+    assert np.array_equal(ow.cpu().numpy().view(np.uint32), ew.view(np.uint32))
+    # end to end like the reference: search 60 neighbours, vote, top 20 items
+    emb = rng.standard_normal((n_sess, 32)).astype(np.float32)
+    index = sss.build_index(emb, 'cos')
+
+    class G(dict):
+        pass
+    dataset = [G(product=type("P", (), {"x": torch.from_numpy(items[item_off[i]:item_off[i + 1]])})()) for i in range(n_sess)]
+    q = emb[7] + 0.01 * rng.standard_normal(32).astype(np.float32)
+    pred = sss.get_prediction_by_knn(torch.from_numpy(q), index, dataset, 60, 20)
+    Dq, Iq = index.search(q[None], 60)
+    ei, _ = oracle.item_vote(Dq, Iq, item_off, items, 20)
+    assert pred == [int(v) for v in ei[0] if v >= 0]
