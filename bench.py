@@ -281,6 +281,7 @@ def main():
 
     ms_total = timed(step_dev_prof, a.steps)
     inner.set_profiling(False)
+    refine_stats = {k: v for k, v in inner.stats().items() if k.startswith("refine_")}
     kernels_per_step = inner.stats()["kernels"] + (1 if world > 1 else 0)
     waves = inner.stats()["waves"]
     reruns = inner.stats()["reruns"]
@@ -381,7 +382,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "waves_per_step": waves, "overflow_reruns": reruns,
+        "waves_per_step": waves, "overflow_reruns": reruns, "refine_volumes_last_step": refine_stats,
         "extra": extra,
     }
     print(json.dumps(out))

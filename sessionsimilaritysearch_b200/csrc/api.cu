@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libsss_b200.so (include/sss_b200.h): handles, workspaces and the wave driver
 // that strings scan -> expand -> refine -> emit together on the caller's stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -174,6 +175,11 @@ struct sss_index {
   size_t ev_used = 0;
   double scan_us = 0.0;
   int64_t scan_launches = 0;
+  // refine of wave w runs on a side stream while the tensor-core scan of wave w+1 is already running
+  unsigned long long* dbg = nullptr;  // device [4], see RefineArgs::debug
+  unsigned long long dbg_host[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_ref[2] = {nullptr, nullptr};
 };
 
 extern "C" const char* sss_last_error(void) { return g_err.c_str(); }
@@ -210,8 +216,14 @@ extern "C" int sss_index_destroy(sss_index_t* ix) {
   ix->sums.release();
   dev_free(ix->seg_off);
   dev_free(ix->row_seg);
+  dev_free(ix->dbg);
   ix->ws.release();
   for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (ix->ev_scan[i]) cudaEventDestroy(ix->ev_scan[i]);
+    if (ix->ev_ref[i]) cudaEventDestroy(ix->ev_ref[i]);
+  }
+  if (ix->side) cudaStreamDestroy(ix->side);
   delete ix;
   return 0;
 }
@@ -226,6 +238,12 @@ extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
     case 2: return ix->stat_reruns;
     case 3: return (int64_t)(ix->scan_us * 1000.0);  // scan-kernel time of the last search, ns (profiling on)
     case 4: return ix->scan_launches;
+    case 5: return (int64_t)ix->dbg_host[0];  // candidates entering refine (profiling on)
+    case 6: return (int64_t)ix->dbg_host[1];  // rows re-scored
+    case 7: return (int64_t)ix->dbg_host[2];  // sessions sorted
+    case 8: return (int64_t)ix->dbg_host[3];  // refine invocations (queries x waves with new candidates)
+    case 9: case 10: case 11: case 12: case 13: case 14: case 15:
+      return (int64_t)ix->dbg_host[4 + (what - 9)];  // cycles of refine phase (what - 9), summed over invocations
     default: return -1;
   }
 }
@@ -362,9 +380,19 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
 
   Bf16ScanPlan plan;
   alignas(64) unsigned char tmap_q[128], tmap_db[128];
+  const char* ov = getenv("SSS_OVERLAP");  // experimental: refine(w) on a side stream under scan(w+1)
+  const bool overlap = tensor && ov && ov[0] == '1';
   if (tensor) {
-    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, &plan)) return 1;
-    if (ws.ensure_records(plan.n_regions, plan.rec_cap)) return 1;
+    // leave shared memory for the refine blocks that co-run with the scan when overlapping
+    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan)) return 1;
+    if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
+    if (overlap && !ix->side) {
+      SSS_CUDA_OK(cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        SSS_CUDA_OK(cudaEventCreateWithFlags(&ix->ev_scan[i], cudaEventDisableTiming));
+        SSS_CUDA_OK(cudaEventCreateWithFlags(&ix->ev_ref[i], cudaEventDisableTiming));
+      }
+    }
     if (make_tensor_map_bf16_2d(tmap_q, ws.q_bf16, (uint64_t)nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
     if (make_tensor_map_bf16_2d(tmap_db, rs.bf16, (uint64_t)n_rows, (uint64_t)ix->d_pad, 128)) return 1;
   }
@@ -386,9 +414,16 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     ra.q_f32 = qdev;
     ra.d = ix->d;
     ra.metric = ix->metric;
+    ra.debug = nullptr;
+    if (ix->profile) {
+      if (!ix->dbg && dev_alloc(&ix->dbg, 12)) return 1;
+      SSS_CUDA_OK(cudaMemsetAsync(ix->dbg, 0, 12 * sizeof(unsigned long long), st));
+      ra.debug = ix->dbg;
+    }
     std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, ix->reduce == SSS_REDUCE_MAX);
     int64_t begin = 0;
     uint32_t wave_id = 0;
+    bool prev_tensor = false;
     for (int64_t end : ends) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (ix->profile) {
@@ -399,31 +434,53 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         }
         e0 = ix->ev[ix->ev_used++];
         e1 = ix->ev[ix->ev_used++];
-        SSS_CUDA_OK(cudaEventRecord(e0, st));
       }
       // The first wave has no threshold: every score is a candidate.  In EXACT mode it is cheaper to get those
       // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
       const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0);
+      const uint32_t w = ++wave_id;
+      const int buf = (int)(w & 1u);
+      HitRecord* rec_buf = ws.rec + (tensor ? (size_t)buf * plan.n_regions * plan.rec_cap : 0);
+      uint32_t* cnt_buf = ws.rec_cnt + (tensor ? (size_t)buf * plan.n_regions : 0);
       ra.rescore = mode == SSS_MODE_EXACT && wave_tensor;
-      ra.wave = ++wave_id;
-      ra.rec = wave_tensor ? ws.rec : nullptr;
-      ra.rec_cnt = ws.rec_cnt;
+      ra.wave = w;
+      ra.rec = wave_tensor ? rec_buf : nullptr;
+      ra.rec_cnt = cnt_buf;
       ra.rec_nsub = tensor ? plan.grid_x * 2 : 0;
       ra.row_limit = n_rows;
+      // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
+      // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever
+      // rise, and refine re-filters every record against the current threshold, so this is still exact).
+      const bool late = overlap && attempt == 0 && wave_tensor && prev_tensor && end - begin >= 524288;
+      if (overlap) {
+        if (w >= 3) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf], 0));                 // records[buf] are free
+        if (w >= 2 && !late) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf ^ 1], 0));    // fresh thresholds
+      }
+      if (e0) SSS_CUDA_OK(cudaEventRecord(e0, st));
       if (wave_tensor) {
-        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, ws.rec, ws.rec_cnt, ws.flags + 1, st))
+        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1, st))
           return 1;
-        if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
-        ix->stat_kernels += 1;
       } else {
         if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, qdev, b.nq, state, st)) return 1;
-        if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
-        ix->stat_kernels += 1;
       }
-      if (launch_refine(ra, state, ix->num_sms, st)) return 1;
+      if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
+      ix->stat_kernels += 1;
+      if (overlap) {
+        SSS_CUDA_OK(cudaEventRecord(ix->ev_scan[buf], st));
+        SSS_CUDA_OK(cudaStreamWaitEvent(ix->side, ix->ev_scan[buf], 0));
+        if (launch_refine(ra, state, ix->num_sms, ix->side)) return 1;
+        SSS_CUDA_OK(cudaEventRecord(ix->ev_ref[buf], ix->side));
+      } else {
+        if (launch_refine(ra, state, ix->num_sms, st)) return 1;
+      }
       ix->stat_kernels += b.k <= 256 ? 2 : 1;
       ix->stat_waves += 1;
+      prev_tensor = wave_tensor;
       begin = end;
+    }
+    if (overlap && wave_id >= 1) {
+      SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[wave_id & 1u], 0));
+      if (wave_id >= 2) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[(wave_id & 1u) ^ 1u], 0));
     }
     if (launch_emit(state, b.nq, b.k, ix->metric, ix->id_offset, Ddev, Idev, st)) return 1;
     ix->stat_kernels += 1;
@@ -433,6 +490,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       SSS_CUDA_OK(cudaMemcpyAsync(b.D, Ddev, (size_t)b.nq * b.k * sizeof(float), cudaMemcpyDeviceToHost, st));
       SSS_CUDA_OK(cudaMemcpyAsync(b.I, Idev, (size_t)b.nq * b.k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
+    if (ix->profile && ix->dbg)
+      SSS_CUDA_OK(cudaMemcpyAsync(ix->dbg_host, ix->dbg, sizeof(ix->dbg_host), cudaMemcpyDeviceToHost, st));
     SSS_CUDA_OK(cudaStreamSynchronize(st));
     if (ix->profile) {
       for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
@@ -661,7 +720,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     RefineArgs ra;
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
-    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.row_limit = ix->n;
+    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.row_limit = ix->n; ra.debug = nullptr;
     std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
     int64_t begin = 0;
     for (int64_t end : ends) {

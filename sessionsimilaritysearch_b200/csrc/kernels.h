@@ -34,7 +34,7 @@ struct Bf16ScanPlan {
   int n_regions;    // record sub-regions: nq_pad * grid_x * 2
   bool ts;          // query tiles resident in TMEM (A operand from TMEM) instead of shared memory
 };
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan);
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
@@ -58,6 +58,7 @@ struct RefineArgs {
   const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
   int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
   int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill
+  unsigned long long* debug; // optional [12]: sums of candidates, re-scored rows, sessions, refines, then cycles per refine phase
 };
 // group by session, (EXACT) prune + re-score survivors, keep the best k, raise the threshold
 int launch_refine(const RefineArgs& a, SelectState st, int num_sms, cudaStream_t stream);

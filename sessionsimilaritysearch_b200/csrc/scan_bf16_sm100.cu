@@ -598,7 +598,7 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
   return 0;
 }
 
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan) {
   SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 128, "tensor-core scan supports d <= 128");
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
@@ -615,6 +615,7 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, Bf16ScanPlan* plan) {
   const int avail = 227 * 1024 - 1024 - kBarrierBytes - q_bytes;
   int stages = avail / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > max_stages) stages = max_stages;
   SSS_REQUIRE(stages >= 2, "not enough shared memory for the DB tile ring");
   plan->num_stages = stages;
   plan->smem_bytes = 1024 + q_bytes + stages * stage_bytes + kBarrierBytes;

@@ -49,10 +49,38 @@ __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   }
 }
 
-template <int SLOT_BITS, int SURV, int KMAX, int RSW, int KC, int THREADS, int RMAX, bool LAST>
+// Descending sort of n distinct non-zero keys in e[0, n) (zero padded to P by the caller for the bitonic path).
+// Small inputs are sorted by rank counting: every thread reads all keys (shared-memory broadcasts), counts the
+// larger ones and scatters its own key to that rank through `tmp` — two barriers instead of ~40.
+__device__ __forceinline__ void sort_desc(uint64_t* e, uint64_t* tmp, int n, int P) {
+  if (n <= 32 && tmp != nullptr) {  // rank counting only pays for tiny inputs (instruction count, measured)
+    uint64_t mine[4];
+    int rank[4];
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n && cnt < 4; i += blockDim.x, ++cnt) {
+      mine[cnt] = e[i];
+      rank[cnt] = 0;
+    }
+    for (int j = 0; j < n; ++j) {
+      const uint64_t v = e[j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < cnt) rank[c] += v > mine[c] ? 1 : 0;
+    }
+    for (int c = 0; c < cnt; ++c) tmp[rank[c]] = mine[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e[i] = tmp[i];
+    __syncthreads();
+    return;
+  }
+  bitonic_desc(e, P);
+}
+
+template <int SLOT_BITS, int NC, int SURV, int KMAX, int RSW, int KC, int THREADS, int RMAX, bool LAST>
 struct RefineCfg {
   static constexpr int kSlotBits = SLOT_BITS;
   static constexpr int kSlots = 1 << SLOT_BITS;  // hash slots = max distinct sessions per query and wave
+  static constexpr int kNc = NC;                 // max new candidates per query and wave
   static constexpr int kSurv = SURV;             // max rows re-scored per query and wave
   static constexpr int kKmax = KMAX;             // max k (retained entries)
   static constexpr int kRsw = RSW;               // re-scoring warps
@@ -68,8 +96,8 @@ struct RefineCfg {
     return (s > a ? s : a) + 8;
   }
   static constexpr size_t smem_bytes(int d_round, bool rescore) {
-    return scratch_bytes() + (size_t)kSlots * 8 + (size_t)SURV * 4 + 16 + (size_t)SURV * 2 + (size_t)KMAX * 2 + 8 +
-           sizeof(float) * (rescore ? d_round : 0);
+    return scratch_bytes() + 4096 + (size_t)kSlots * 8 + (size_t)NC * 8 + 16 + (size_t)NC * 2 + (size_t)SURV * 2 +
+           (size_t)KMAX * 2 + 8 + sizeof(float) * (rescore ? d_round : 0);
   }
 };
 
@@ -77,31 +105,36 @@ enum { RF_DONE = 0, RF_SKIP = 1 };
 
 template <class C>
 struct RefineSmem {
-  uint64_t* A;          // [slots] gather + sort
-  uint32_t* owner;      // [slots] session + 1
-  uint32_t* best;       // [slots] max key
-  uint32_t* surv_row;   // [SURV]
+  uint64_t* A;          // [slots] gather + sort (overlays the scratch below)
+  uint64_t* tmp;        // [512] rank-sort staging
   uint32_t* recptr;     // [RMAX] global record index
   uint32_t* subpre;     // [kMaxSub + 1]
-  int* ctr;             // [4] s_nsurv, s_H, s_uniq, s_fail
-  uint16_t* surv_slot;  // [SURV]
-  uint16_t* ret_slot;   // [KMAX]
   float* tiles;         // [RSW][32][KC+1]
+  uint32_t* owner;      // [slots] session + 1
+  uint32_t* best;       // [slots] max key
+  uint32_t* ent_key;    // [NC] compacted new candidates
+  uint32_t* ent_row;    // [NC]
+  int* ctr;             // [4] n_ent, n_surv, H, uniq / fail
+  uint16_t* ent_slot;   // [NC]
+  uint16_t* surv;       // [SURV] entry index of the rows to re-score
+  uint16_t* ret_slot;   // [KMAX]
   float* qs;            // [d_round]
   __device__ explicit RefineSmem(unsigned char* p) {
-    // scratch first (8-byte aligned): A overlays recptr/subpre/tiles
     A = reinterpret_cast<uint64_t*>(p);
     recptr = reinterpret_cast<uint32_t*>(p);
     subpre = recptr + C::kRmax;
     tiles = reinterpret_cast<float*>(subpre + C::kMaxSub + 2);
-    unsigned char* rest = p + C::scratch_bytes();
+    tmp = reinterpret_cast<uint64_t*>(p + C::scratch_bytes());
+    unsigned char* rest = p + C::scratch_bytes() + 4096;
     owner = reinterpret_cast<uint32_t*>(rest);
     best = owner + C::kSlots;
-    surv_row = best + C::kSlots;
-    ctr = reinterpret_cast<int*>(surv_row + C::kSurv);
-    surv_slot = reinterpret_cast<uint16_t*>(ctr + 4);
-    ret_slot = surv_slot + C::kSurv;
-    qs = reinterpret_cast<float*>(ret_slot + C::kKmax + ((C::kSurv + C::kKmax) & 1));
+    ent_key = best + C::kSlots;
+    ent_row = ent_key + C::kNc;
+    ctr = reinterpret_cast<int*>(ent_row + C::kNc);
+    ent_slot = reinterpret_cast<uint16_t*>(ctr + 4);
+    surv = ent_slot + C::kNc;
+    ret_slot = surv + C::kSurv;
+    qs = reinterpret_cast<float*>(ret_slot + C::kKmax + ((C::kNc + C::kSurv + C::kKmax) & 1));
   }
 };
 
@@ -112,85 +145,48 @@ __device__ __forceinline__ int rf_insert(const RefineSmem<C>& sm, uint32_t sess)
   for (int probe = 0; probe < C::kSlots; ++probe) {
     const uint32_t prev = atomicCAS(&sm.owner[h], 0u, sess + 1u);
     if (prev == 0u) {
-      atomicAdd(&sm.ctr[2], 1);
+      atomicAdd(&sm.ctr[3], 1);
       return (int)h;
     }
     if (prev == sess + 1u) return (int)h;
     h = (h + 1u) & (C::kSlots - 1);
   }
-  sm.ctr[3] = 1;
-  return -1;
-}
-template <class C>
-__device__ __forceinline__ int rf_find(const RefineSmem<C>& sm, uint32_t sess) {
-  uint32_t h = (sess * 2654435761u) >> (32 - C::kSlotBits);
-  for (int probe = 0; probe < C::kSlots; ++probe) {
-    const uint32_t o = sm.owner[h];
-    if (o == sess + 1u) return (int)h;
-    if (o == 0u) return -1;
-    h = (h + 1u) & (C::kSlots - 1);
-  }
+  atomicOr(&sm.ctr[3], 0x40000000);
   return -1;
 }
 
-// stream the new candidates of query q through f(key, row, session); four independent loads (and session
-// gathers) are in flight per thread, consecutive threads read consecutive scores of a record
-template <class C, class F>
-__device__ __forceinline__ void rf_for_each(const RefineArgs& a, const SelectState& st, const RefineSmem<C>& sm,
-                                            const uint64_t* g, int nr, int n, int Rc, float thr, F f) {
-  constexpr int U = 4;
-  if (a.rec != nullptr) {
-    const int total = Rc * 32;
-    for (int t0 = threadIdx.x; t0 < total; t0 += U * C::kThreads) {
-      float v[U];
-      uint32_t row[U], sess[U];
-      bool pass[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = t0 + u * C::kThreads;
-        pass[u] = t < total;
-        const HitRecord* r = a.rec + sm.recptr[pass[u] ? (t >> 5) : 0];
-        v[u] = r->v[t & 31];
-        row[u] = r->row_base + (uint32_t)(t & 31);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        pass[u] = pass[u] && v[u] > thr && (int64_t)row[u] < a.row_limit;
-        sess[u] = (pass[u] && a.reduce_max) ? (uint32_t)a.row_seg[row[u]] : row[u];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (pass[u]) f(score_key(v[u]), row[u], sess[u]);
-    }
-  } else {
-    for (int i0 = nr + threadIdx.x; i0 < n; i0 += U * C::kThreads) {
-      uint64_t e[U];
-      uint32_t sess[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * C::kThreads;
-        e[u] = i < n ? g[i] : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        sess[u] = (e[u] != 0ull && a.reduce_max) ? (uint32_t)a.row_seg[cand_id(e[u])] : cand_id(e[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (e[u] != 0ull) f(cand_key(e[u]), cand_id(e[u]), sess[u]);
-    }
-  }
+// warp-aggregated append: lanes with `pass` get consecutive positions after *counter
+__device__ __forceinline__ int warp_append(int* counter, bool pass) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+  if (bal == 0u) return -1;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == (__ffs(bal) - 1)) base = atomicAdd(counter, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  return pass ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
+
+// optional per-phase cycle accounting of thread 0 (a.debug[4 + phase], profiling builds of the statistics only)
+#define RF_PHASE(i)                                                              \
+  do {                                                                           \
+    if (a.debug != nullptr && threadIdx.x == 0) {                                \
+      const long long _t = clock64();                                            \
+      atomicAdd(&a.debug[4 + (i)], (unsigned long long)(_t - _t0));              \
+      _t0 = _t;                                                                  \
+    }                                                                            \
+  } while (0)
 
 template <class C>
 __device__ int refine_query(const RefineArgs& a, const SelectState& st, const RefineSmem<C>& sm, int q) {
+  long long _t0 = clock64();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = C::kThreads / 32;
   const int nr = (int)st.nret[q];
   uint64_t* g = st.cand + (size_t)q * st.cap;
   const float margin = st.margin[q];
   const float thr = st.thr[q];
   const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
-  int n = nr, Rc = 0;
 
   __syncthreads();  // previous query of a persistent block is fully done with shared memory
   for (int h = tid; h < C::kSlots; h += C::kThreads) {
@@ -201,6 +197,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   if (tid == 0) sm.subpre[0] = 0u;
   __syncthreads();
 
+  // ---- A. compact the new candidates into shared memory
   if (a.rec != nullptr) {
     const int nsub = a.rec_nsub;
     const size_t sub0 = (size_t)q * nsub;
@@ -225,27 +222,61 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
       }
     }
     __syncthreads();
+    RF_PHASE(0);  // init + sub-region counts
     const int R = (int)sm.subpre[nsub];
     if (R == 0) return RF_DONE;  // nothing new since the last refine
     if (R > C::kRmax) {
       if (!C::kLast) return RF_SKIP;
       if (tid == 0) *st.overflow = 1;
     }
-    Rc = R < C::kRmax ? R : C::kRmax;
+    const int Rc = R < C::kRmax ? R : C::kRmax;
     for (int s = tid; s < nsub; s += C::kThreads) {
       const uint32_t b0 = sm.subpre[s], b1 = sm.subpre[s + 1];
       for (uint32_t j = b0; j < b1 && j < (uint32_t)C::kRmax; ++j)
         sm.recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
     }
+    __syncthreads();
+    // a warp takes four records per round: four independent 128-byte loads in flight, lane = score index
+    constexpr int RU = 4;
+    for (int r0 = warp * RU; r0 < Rc; r0 += NW * RU) {
+      float v[RU];
+      uint32_t row[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const HitRecord* r = a.rec + sm.recptr[r0 + u < Rc ? r0 + u : r0];
+        v[u] = r->v[lane];
+        row[u] = r->row_base + (uint32_t)lane;
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const bool pass = r0 + u < Rc && v[u] > thr && (int64_t)row[u] < a.row_limit;
+        const int pos = warp_append(&sm.ctr[0], pass);
+        if (pos >= 0 && pos < C::kNc) {
+          sm.ent_key[pos] = score_key(v[u]);
+          sm.ent_row[pos] = row[u];
+        }
+      }
+    }
   } else {
     const uint32_t c = st.cnt[q];
-    n = c > (uint32_t)st.cap ? st.cap : (int)c;
+    const int n = c > (uint32_t)st.cap ? st.cap : (int)c;
     if (c > (uint32_t)st.cap && tid == 0) *st.overflow = 1;
     if (n == nr) return RF_DONE;  // nothing new since the last refine
+    if (n - nr > C::kNc) {
+      if (!C::kLast) return RF_SKIP;
+    }
+    for (int i = nr + tid; i < n; i += C::kThreads) {
+      const uint64_t e = g[i];
+      if (i - nr < C::kNc) {
+        sm.ent_key[i - nr] = cand_key(e);
+        sm.ent_row[i - nr] = cand_id(e);
+      }
+    }
+    if (tid == 0) sm.ctr[0] = n - nr;
   }
   if (a.rescore)
     for (int j = tid; j < d_round; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
-  // retained entries first: they own their slots and keep their (final) keys
+  // retained entries own their slots and keep their (final) keys
   for (int i = tid; i < nr; i += C::kThreads) {
     const uint64_t e = g[i];
     const int h = rf_insert<C>(sm, cand_id(e));
@@ -253,33 +284,58 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     sm.ret_slot[i] = (uint16_t)(h >= 0 ? h : 0);
   }
   __syncthreads();
-
-  // 1. group the new candidates by session
-  rf_for_each<C>(a, st, sm, g, nr, n, Rc, thr, [&](uint32_t key, uint32_t row, uint32_t sess) {
-    const int h = rf_insert<C>(sm, sess);
-    if (h >= 0) atomicMax(&sm.best[h], key);
-  });
-  __syncthreads();
-  if (sm.ctr[3] != 0 || sm.ctr[2] > C::kSlots * 3 / 4) {
+  RF_PHASE(1);  // record compaction + retained insert
+  int n_ent = sm.ctr[0];
+  if (n_ent > C::kNc) {
     if (!C::kLast) return RF_SKIP;
-    if (sm.ctr[3] != 0 && tid == 0) *st.overflow = 1;  // table full: candidates were dropped
+    if (tid == 0) *st.overflow = 1;
+    n_ent = C::kNc;
+  }
+
+  // ---- B. group by session (four session gathers in flight per thread)
+  for (int i0 = tid; i0 < n_ent; i0 += 4 * C::kThreads) {
+    uint32_t sess[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * C::kThreads;
+      const uint32_t row = sm.ent_row[i < n_ent ? i : i0];
+      sess[u] = a.reduce_max ? (uint32_t)a.row_seg[row] : row;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * C::kThreads;
+      if (i < n_ent) {
+        const int h = rf_insert<C>(sm, sess[u]);
+        if (h >= 0) atomicMax(&sm.best[h], sm.ent_key[i]);
+        sm.ent_slot[i] = (uint16_t)(h >= 0 ? h : 0);
+      }
+    }
+  }
+  __syncthreads();
+  RF_PHASE(2);  // session hash
+  {
+    const int uniq = sm.ctr[3];
+    if ((uniq & 0x40000000) != 0 || (uniq & 0x3FFFFFFF) > C::kSlots * 3 / 4) {
+      if (!C::kLast) return RF_SKIP;
+      if ((uniq & 0x40000000) != 0 && tid == 0) *st.overflow = 1;  // table full: candidates were dropped
+    }
   }
 
   if (a.rescore) {
-    // 2a. survivors among the new rows
-    rf_for_each<C>(a, st, sm, g, nr, n, Rc, thr, [&](uint32_t key, uint32_t row, uint32_t sess) {
-      const int h = rf_find<C>(sm, sess);
-      if (h < 0) return;
-      if (key_score(key) >= key_score(sm.best[h]) - 2.0f * margin) {
-        const int pos = atomicAdd(&sm.ctr[0], 1);
-        if (pos < C::kSurv) {
-          sm.surv_row[pos] = row;
-          sm.surv_slot[pos] = (uint16_t)h;
-        }
+    const float t_lo = -INFINITY;  // (a session-level pre-selection costs more instructions than it saves)
+    // ---- C. survivors: rows of live sessions within 2 * margin of their session's best tensor-core score
+    for (int i0 = warp * 32; i0 < n_ent; i0 += C::kThreads) {
+      const int i = i0 + lane;
+      bool keep = false;
+      if (i < n_ent) {
+        const float sb = key_score(sm.best[sm.ent_slot[i]]);
+        keep = sb >= t_lo && key_score(sm.ent_key[i]) >= sb - 2.0f * margin;
       }
-    });
+      const int pos = warp_append(&sm.ctr[1], keep);
+      if (pos >= 0 && pos < C::kSurv) sm.surv[pos] = (uint16_t)i;
+    }
     __syncthreads();
-    int nsurv = sm.ctr[0];
+    int nsurv = sm.ctr[1];
     if (nsurv > C::kSurv) {
       if (!C::kLast) return RF_SKIP;
       if (tid == 0) *st.overflow = 1;
@@ -289,18 +345,20 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     for (int h = tid; h < C::kSlots; h += C::kThreads) sm.best[h] = 0u;
     __syncthreads();
     for (int i = tid; i < nr; i += C::kThreads) atomicMax(&sm.best[sm.ret_slot[i]], cand_key(g[i]));
-    // 2b. exact fixed-order re-scoring of the survivors
+    RF_PHASE(4);  // survivors + reset
+    // ---- D. exact fixed-order re-scoring of the survivors
     if (warp < C::kRsw) {
       constexpr int LPR = C::kKc / 4;   // lanes per row segment (float4 each)
       constexpr int RPI = 32 / LPR;     // rows per load instruction
+      constexpr int NL = 32 / RPI;      // load instructions per tile
       float* tile = sm.tiles + (size_t)warp * 32 * (C::kKc + 1);
       const int rsub = lane / LPR, c4 = lane % LPR;
-      constexpr int NL = 32 / RPI;      // load instructions per tile
       const bool vec_ok = (a.d & 3) == 0;
       for (int base = warp * 32; base < nsurv; base += C::kRsw * 32) {
         const int li = base + lane;
         const bool live = li < nsurv;
-        const uint32_t my_row = live ? sm.surv_row[li] : 0u;
+        const int ei = live ? (int)sm.surv[li] : 0;
+        const uint32_t my_row = live ? sm.ent_row[ei] : 0u;
         const float* rowp[NL];
 #pragma unroll
         for (int t = 0; t < NL; ++t)
@@ -349,27 +407,39 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
             for (int t = 0; t < NL; ++t) cur[t] = nxt[t];
           }
         }
-        if (live) atomicMax(&sm.best[sm.surv_slot[li]], score_key(a.metric == 0 ? acc : -acc));
+        if (live) atomicMax(&sm.best[sm.ent_slot[ei]], score_key(a.metric == 0 ? acc : -acc));
       }
     }
-    __syncthreads();
   }
 
-  // 3. one entry per session, best k of them (A overlays the record scratch: every pass is finished)
+  // ---- E. one entry per session, best k of them (A overlays the record scratch: every pass is finished)
   __syncthreads();
-  for (int h = tid; h < C::kSlots; h += C::kThreads) {
-    const uint32_t o = sm.owner[h];
-    if (o != 0u && sm.best[h] != 0u) sm.A[atomicAdd(&sm.ctr[1], 1)] = pack_cand(sm.best[h], o - 1u);
+  RF_PHASE(5);  // re-scoring
+  // with k retained entries the old k-th key is a floor: every retained entry is >= it, a new session below it
+  // cannot enter (a tie loses on the id) — dropping those here keeps the sort at ~k + newcomers elements
+  const uint32_t floor_key = nr == a.k ? cand_key(g[a.k - 1]) : 0u;
+  for (int h0 = warp * 32; h0 < C::kSlots; h0 += C::kThreads) {
+    const int h = h0 + lane;
+    const uint32_t o = sm.owner[h], bk = sm.best[h];
+    const int pos = warp_append(&sm.ctr[2], o != 0u && bk != 0u && bk >= floor_key);
+    if (pos >= 0) sm.A[pos] = pack_cand(bk, o - 1u);
   }
   __syncthreads();
-  const int H = sm.ctr[1];
+  const int H = sm.ctr[2];
   int P = 2;
   while (P < H) P <<= 1;
   for (int i = H + tid; i < P; i += C::kThreads) sm.A[i] = 0ull;
   __syncthreads();
-  bitonic_desc(sm.A, P);
+  sort_desc(sm.A, sm.tmp, H, P);
   const int m = H < a.k ? H : a.k;
   for (int i = tid; i < m; i += C::kThreads) g[i] = sm.A[i];
+  if (tid == 0 && a.debug != nullptr) {  // volume counters for tuning (sss_index_stat 5..8)
+    atomicAdd(&a.debug[0], (unsigned long long)n_ent);
+    atomicAdd(&a.debug[1], (unsigned long long)sm.ctr[1]);
+    atomicAdd(&a.debug[2], (unsigned long long)H);
+    atomicAdd(&a.debug[3], 1ull);
+  }
+  RF_PHASE(6);  // final gather + sort + write back
   if (tid == 0) {
     st.cnt[q] = m;
     st.nret[q] = m;
@@ -380,7 +450,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
 
 // one block per query; queries that do not fit go on the skip list of this wave
 template <class C>
-__global__ void __launch_bounds__(C::kThreads) refine_small_kernel(RefineArgs a, SelectState st) {
+__global__ void __launch_bounds__(C::kThreads, 4) refine_small_kernel(RefineArgs a, SelectState st) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
   RefineSmem<C> sm(rf_smem);
   const int q = blockIdx.x;
@@ -401,8 +471,8 @@ __global__ void __launch_bounds__(C::kThreads) refine_large_kernel(RefineArgs a,
   }
 }
 
-using RefineSmall = RefineCfg<10, 1024, 512, 4, 16, 256, 512, false>;
-using RefineLarge = RefineCfg<12, 4096, 2048, 6, 32, 512, 4096, true>;
+using RefineSmall = RefineCfg<10, 1536, 768, 512, 4, 16, 256, 512, false>;
+using RefineLarge = RefineCfg<12, 4096, 4096, 2048, 16, 16, 512, 4096, true>;
 
 int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStream_t stream) {
   RefineArgs a = a_in;

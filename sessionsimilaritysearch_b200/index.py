@@ -112,7 +112,10 @@ class _FlatIndex:
     def stats(self):
         st = self._lib.sss_index_stat
         return {"kernels": int(st(self._h, 0)), "waves": int(st(self._h, 1)), "reruns": int(st(self._h, 2)),
-                "scan_ns": int(st(self._h, 3)), "scan_launches": int(st(self._h, 4))}
+                "scan_ns": int(st(self._h, 3)), "scan_launches": int(st(self._h, 4)),
+                "refine_candidates": int(st(self._h, 5)), "refine_rescored": int(st(self._h, 6)),
+                "refine_sessions": int(st(self._h, 7)), "refine_calls": int(st(self._h, 8)),
+                "refine_phase_cycles": [int(st(self._h, 9 + p)) for p in range(7)]}
 
 
 class IndexFlatIP(_FlatIndex):

@@ -96,3 +96,59 @@ def test_item_vote_and_get_prediction_by_knn(oracle):
     Dq, Iq = index.search(q[None], 60)
     ei, _ = oracle.item_vote(Dq, Iq, item_off, items, 20)
     assert pred == [int(v) for v in ei[0] if v >= 0]
+
+
+def test_end_to_end_sessions_to_topk(oracle):
+    """BASELINE config 1 in miniature (test_amazon_filterd.py:485-578): DB = encode(prefix + suffix), queries =
+    encode(prefix), cosine top-k — CUDA encoder + CUDA search against oracle encoder + oracle search."""
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from sessionsimilaritysearch_b200 import graph, sessions, synth
+    in_dim, hidden, n_layers, out_dim, msl = 64, 96, 3, 200, 20
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 21)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    tok = synth.HashTokenizer()
+    rng = np.random.default_rng(22)
+    full = synth.make_sessions(600, 23)
+    pairs = [synth.split_session(s, rng) for s in full]
+
+    def graphs_of(seqs):
+        out = []
+        for s, t in seqs:
+            g = sessions.sequence_to_graph(0, s, t, tok, 20)
+            g['query'].x = synth.text_features(g['query'].input_ids, in_dim)
+            g['product'].input_ids = synth.text_features(g['product'].input_ids, in_dim)
+            out.append(g)
+        return out
+
+    db_graphs = graphs_of([(p + s, s) for p, s in pairs])
+    q_graphs = graphs_of(pairs[:100])
+
+    def encode(gs, fn):
+        return np.concatenate([fn(b) for b in graph.DataLoader(gs, batch_size=200, shuffle=False)], 0)
+
+    cuda_fn = lambda b: enc(b.to("cuda")).cpu().numpy()
+    cpu_fn = lambda b: eo.encoder_forward(P, eo.batch_from_pyg(b), n_layers).numpy()
+    db_gpu, q_gpu = encode(db_graphs, cuda_fn), encode(q_graphs, cuda_fn)
+    db_cpu, q_cpu = encode(db_graphs, cpu_fn), encode(q_graphs, cpu_fn)
+    np.testing.assert_allclose(db_gpu, db_cpu, rtol=3e-4, atol=3e-4 * float(np.abs(db_cpu).max()))
+    index = sss.build_index(db_gpu, 'cos')
+    D, I = index.search(sss.normalize(q_gpu), 20)
+    Do, Io = oracle.search_flat(oracle.normalize(db_cpu, 1), oracle.normalize(q_cpu, 1), 20)
+    recall = np.mean([len(set(I[r]) & set(Io[r])) / 20.0 for r in range(100)])
+    assert recall >= 0.99, recall
+    assert np.max(np.abs(D - Do)) < 1e-3
+    # on identical embeddings the search itself is exact (d = 200 takes the fp32 scan)
+    D2, I2 = oracle.search_flat(oracle.normalize(db_gpu, 1), oracle.normalize(q_gpu, 1), 20)
+    assert np.array_equal(I, I2) and np.array_equal(D.view(np.uint32), D2.view(np.uint32))
+    # hashed retrieval (fine_tune_ours.py:826-876): sign head -> packed codes -> Hamming top-k
+    g = torch.Generator().manual_seed(5)
+    W, b = torch.randn(250, out_dim, generator=g) / out_dim ** 0.5, torch.randn(250, generator=g) * 0.1
+    head = sss.BinarizeHead(W, b)
+    dcodes = sss.pack_sign_bits(head(torch.from_numpy(db_gpu)))
+    qcodes = sss.pack_sign_bits(head(torch.from_numpy(q_gpu)))
+    bi = sss.IndexBinaryFlat(256)
+    bi.add(dcodes)
+    Dh, Ih = bi.search(qcodes, 20)
+    Dho, Iho = oracle.search_hamming(dcodes.cpu().numpy(), qcodes.cpu().numpy(), 20)
+    assert np.array_equal(Dh.cpu().numpy(), Dho) and np.array_equal(Ih.cpu().numpy(), Iho)

@@ -45,9 +45,9 @@ def test_normalize_bit_exact_and_golden(sss, oracle, d):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "exact"])
-@pytest.mark.parametrize("d", [7, 64, 100, 128, 200])
+@pytest.mark.parametrize("d", [7, 64, 100, 128, 200, 768, 1600])
 def test_flat_ip_bit_exact(sss, oracle, mode, d):
-    db = make_iid(20000, d, 1)
+    db = make_iid(20000 if d <= 256 else 3000, d, 1)
     q = make_iid(33, d, 2)
     ix = sss.build_index(db, 'cos', mode=mode)
     qn = sss.normalize(q)
@@ -55,7 +55,7 @@ def test_flat_ip_bit_exact(sss, oracle, mode, d):
     dbn = oracle.normalize(db, oracle.NORM_UTIL)
     Do, Io = oracle.search_flat(dbn, oracle.normalize(q, oracle.NORM_UTIL), 100)
     _assert_exact(D, I, Do, Io)
-    assert ix.ntotal == 20000 and ix.stats()["reruns"] == 0
+    assert ix.ntotal == db.shape[0] and ix.stats()["reruns"] == 0
 
 
 @pytest.mark.parametrize("mode", ["fp32", "exact"])
