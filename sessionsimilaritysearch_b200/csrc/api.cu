@@ -53,6 +53,8 @@ struct Workspace {
   int64_t* out_I = nullptr;
   HitRecord* rec = nullptr;
   uint32_t* rec_cnt = nullptr;
+  float* cmax = nullptr;      // bootstrap chunk maxima [n_chunks, nq_pad]
+  size_t cmax_elems = 0;
   size_t rec_entries = 0;
   int n_regions = 0;
   int64_t out_elems = 0;
@@ -101,7 +103,8 @@ struct Workspace {
   }
   void release() {
     release_query_side();
-    dev_free(flags); dev_free(out_D); dev_free(out_I); dev_free(rec); dev_free(rec_cnt);
+    dev_free(flags); dev_free(out_D); dev_free(out_I); dev_free(rec); dev_free(rec_cnt); dev_free(cmax);
+    cmax_elems = 0;
     nq_pad = 0; cap = 0; rec_entries = 0; n_regions = 0; out_elems = 0;
   }
   SelectState state() const {
@@ -165,6 +168,7 @@ struct sss_index {
   RowStore sums;      // per-segment sums (reduce == SUM)
   int reduce = 0;
   int64_t n_seg = 0;
+  int64_t max_seg_len = 1;
   int64_t* seg_off = nullptr;  // device
   int32_t* row_seg = nullptr;  // device
   Workspace ws;
@@ -296,8 +300,12 @@ extern "C" int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, i
   }
   SSS_REQUIRE(seg_off != nullptr && n_seg >= 1, "sss_index_set_segments: need seg_off[n_seg+1]");
   SSS_REQUIRE(seg_off[0] == 0 && seg_off[n_seg] == ix->rows.n, "sss_index_set_segments: seg_off must span [0, ntotal]");
-  for (int64_t s = 0; s < n_seg; ++s)
+  int64_t max_len = 1;
+  for (int64_t s = 0; s < n_seg; ++s) {
     SSS_REQUIRE(seg_off[s + 1] >= seg_off[s], "sss_index_set_segments: seg_off must be non-decreasing");
+    max_len = std::max(max_len, seg_off[s + 1] - seg_off[s]);
+  }
+  ix->max_seg_len = max_len;
   dev_free(ix->seg_off);
   dev_free(ix->row_seg);
   if (dev_alloc(&ix->seg_off, n_seg + 1) || dev_alloc(&ix->row_seg, ix->rows.n)) return 1;
@@ -326,8 +334,18 @@ namespace sss {
 
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
-static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups = false) {
+static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups = false,
+                                       int64_t bootstrap_rows = 0) {
   std::vector<int64_t> ends;
+  if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): start at half of it
+    int64_t e = bootstrap_rows / 2;
+    ends.push_back(e);
+    while (e < n_rows) {
+      e = std::min(n_rows, 2 * e);
+      ends.push_back(e);
+    }
+    return ends;
+  }
   int64_t first = std::max<int64_t>(128, (std::min<int64_t>(cap / 2, cap - k) / 128) * 128);
   if (first > 2048) first = 2048;
   // without session grouping every row is its own group: a shorter threshold-less first wave keeps the
@@ -420,7 +438,29 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       SSS_CUDA_OK(cudaMemsetAsync(ix->dbg, 0, 12 * sizeof(unsigned long long), st));
       ra.debug = ix->dbg;
     }
-    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, ix->reduce == SSS_REDUCE_MAX);
+    // Bootstrap: one tensor-core pass in chunk-max mode over the first 128K rows gives every query a valid
+    // threshold at once and replaces the first five doubling waves (and, in EXACT mode, the fp32 first wave).
+    const int64_t kBootRows = 131072;
+    const int n_boot_chunks = (int)(kBootRows / 32);
+    const bool grouped = ix->reduce == SSS_REDUCE_MAX;
+    const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
+    const char* no_boot = getenv("SSS_NO_BOOTSTRAP");
+    const bool bootstrap = tensor && plan.ts && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
+                           (int64_t)(b.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4;
+    if (bootstrap) {
+      const size_t need = (size_t)n_boot_chunks * (size_t)nq_pad;
+      if (need > ws.cmax_elems) {
+        dev_free(ws.cmax);
+        ws.cmax_elems = need;
+        if (dev_alloc(&ws.cmax, need)) return 1;
+      }
+      if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, 0, kBootRows, state, ws.rec, ws.rec_cnt, ws.flags + 1,
+                           ws.cmax, st))
+        return 1;
+      if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, b.nq, nq_pad, b.k, chunk_gap, 2.0f, state, st)) return 1;
+      ix->stat_kernels += 2;
+    }
+    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, grouped, bootstrap ? kBootRows : 0);
     int64_t begin = 0;
     uint32_t wave_id = 0;
     bool prev_tensor = false;
@@ -437,7 +477,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       }
       // The first wave has no threshold: every score is a candidate.  In EXACT mode it is cheaper to get those
       // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
-      const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0);
+      const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0 && !bootstrap);
       const uint32_t w = ++wave_id;
       const int buf = (int)(w & 1u);
       HitRecord* rec_buf = ws.rec + (tensor ? (size_t)buf * plan.n_regions * plan.rec_cap : 0);
@@ -458,7 +498,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       }
       if (e0) SSS_CUDA_OK(cudaEventRecord(e0, st));
       if (wave_tensor) {
-        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1, st))
+        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1,
+                             nullptr, st))
           return 1;
       } else {
         if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, qdev, b.nq, state, st)) return 1;

@@ -39,7 +39,10 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
-                     int* err_flag, cudaStream_t stream);
+                     int* err_flag, float* cmax, cudaStream_t stream);
+// select.cu — bootstrap thresholds from chunk maxima: thr[q] = just below (2k-th largest chunk max - slack)
+int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
+                         float slack_mult, SelectState st, cudaStream_t stream);
 
 // select.cu
 struct RefineArgs {

@@ -168,6 +168,8 @@ struct ScanParams {
   int rec_cap;
   int* err_flag;
   const uint4* q_bf16;   // [nq_pad, d_pad] bf16, 16-byte aligned rows (TS variant reads it directly)
+  float* cmax;           // bootstrap mode: write the max of every 32-row chunk to cmax[chunk * nq_pad + q] instead
+                         // of filtering (chunk counted from row_begin)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -520,6 +522,11 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
         m2 = max3(m2, f[24], f[25]); m3 = max3(m3, f[26], f[27]);
         m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
         const float mx = fmaxf(max3(m0, m1, m2), m3);
+        if (p.cmax != nullptr) {  // bootstrap pass: chunk maxima only (coalesced: lane = query)
+          const uint32_t chunk = (row_tile - (uint32_t)p.row_begin) / 32u + (uint32_t)c;
+          p.cmax[(size_t)chunk * (size_t)(p.total_mtiles * kTileQ) + qidx] = mx;
+          return;
+        }
         const bool hit = mx > thr;
         if (__any_sync(0xffffffffu, hit)) {
           if (hit) {
@@ -626,7 +633,8 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
 
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
-                     int* err_flag, cudaStream_t stream) {
+                     int* err_flag, float* cmax, cudaStream_t stream) {
+  SSS_REQUIRE(cmax == nullptr || plan.ts, "chunk-max bootstrap needs the TS scan variant");
   SSS_REQUIRE(row_begin % kTileRows == 0, "scan wave must start on a 128-row boundary");
   ScanParams p;
   p.num_kb = plan.num_kb;
@@ -641,6 +649,7 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.rec_cap = plan.rec_cap;
   p.err_flag = err_flag;
   p.q_bf16 = (const uint4*)q_bf16;
+  p.cmax = cmax;
   if (p.n_tiles <= 0) return 0;
   static int smem_set = 0;
   if (smem_set < plan.smem_bytes) {

@@ -443,7 +443,8 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   if (tid == 0) {
     st.cnt[q] = m;
     st.nret[q] = m;
-    st.thr[q] = m == a.k ? key_score(cand_key(sm.A[a.k - 1])) - margin : -INFINITY;
+    // thresholds only ever rise (a bootstrap threshold may already be in place while fewer than k sessions passed)
+    st.thr[q] = m == a.k ? fmaxf(thr, key_score(cand_key(sm.A[a.k - 1])) - margin) : thr;
   }
   return RF_DONE;
 }
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(C::kThreads) refine_large_kernel(RefineArgs a,
   }
 }
 
-using RefineSmall = RefineCfg<10, 1536, 768, 512, 4, 16, 256, 512, false>;
+using RefineSmall = RefineCfg<10, 1536, 768, 512, 8, 16, 256, 512, false>;
 using RefineLarge = RefineCfg<12, 4096, 4096, 2048, 16, 16, 512, 4096, true>;
 
 int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStream_t stream) {
@@ -503,6 +504,47 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
   }
   int grid = (int)std::min<int64_t>(a.nq, num_sms);
   refine_large_kernel<RefineLarge><<<grid, RefineLarge::kThreads, smem, stream>>>(a, st);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- bootstrap thresholds ---------------------------------------------------------------------------------
+// A tensor-core pass in chunk-max mode left cmax[chunk, q] = max score of 32 consecutive rows.  Among the
+// (k-1) * gap + 1 largest chunk maxima of a query one can pick k chunks that are pairwise >= gap chunks apart,
+// i.e. (with gap = floor((max session length + 30) / 32) + 1, or 1 without sessions) k rows of k DISTINCT
+// sessions/rows whose scores are >= T, the smallest of those maxima.  So the k-th best exact session score is >= T - margin and a row
+// can only matter if its tensor-core score is >= T - 2 * margin: thr = the float just below that.
+__global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq_pad,
+                                                            int k, int chunk_gap, float slack_mult, SelectState st) {
+  extern __shared__ uint64_t bs_keys[];  // [P]
+  const int q = blockIdx.x;
+  int P = 2;
+  while (P < n_chunks) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    bs_keys[i] = i < n_chunks ? (((uint64_t)score_key(cmax[(size_t)i * nq_pad + q]) << 32) | (uint64_t)(uint32_t)i) : 0ull;
+  __syncthreads();
+  bitonic_desc(bs_keys, P);
+  if (threadIdx.x == 0) {
+    // of the `need` largest chunks, taken in index order, every gap-th one is >= gap chunks from the previous pick
+    const int need = (k - 1) * chunk_gap + 1;
+    if (need <= n_chunks) {
+      const float T = key_score((uint32_t)(bs_keys[need - 1] >> 32));
+      st.thr[q] = nextafterf(T - slack_mult * st.margin[q], -INFINITY);
+    }
+  }
+}
+
+int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
+                         float slack_mult, SelectState st, cudaStream_t stream) {
+  int P = 2;
+  while (P < n_chunks) P <<= 1;
+  SSS_REQUIRE(P <= 8192, "bootstrap region too large");
+  static bool attr = false;
+  if (!attr) {
+    SSS_CUDA_OK(cudaFuncSetAttribute(bootstrap_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    attr = true;
+  }
+  bootstrap_thr_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(cmax, n_chunks, nq_pad, k, chunk_gap, slack_mult, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
