@@ -248,6 +248,12 @@ extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
     case 8: return (int64_t)ix->dbg_host[3];  // refine invocations (queries x waves with new candidates)
     case 9: case 10: case 11: case 12: case 13: case 14: case 15:
       return (int64_t)ix->dbg_host[4 + (what - 9)];  // cycles of refine phase (what - 9), summed over invocations
+    case 16: case 17: case 18: case 19: case 20: case 21: case 22: case 23: {  // scan role wait cycles (SSS_SCAN_PROF experiments)
+      unsigned long long h[8] = {0};
+      if (!scan_prof_buffer()) return -1;
+      cudaMemcpy(h, scan_prof_buffer(), sizeof(h), cudaMemcpyDeviceToHost);
+      return (int64_t)h[what - 16];
+    }
     default: return -1;
   }
 }
@@ -445,7 +451,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     const bool grouped = ix->reduce == SSS_REDUCE_MAX;
     const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
     const char* no_boot = getenv("SSS_NO_BOOTSTRAP");
-    const bool bootstrap = tensor && plan.ts && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
+    const bool bootstrap = tensor && (plan.ts || plan.two_cta) && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
                            (int64_t)(b.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4;
     if (bootstrap) {
       const size_t need = (size_t)n_boot_chunks * (size_t)nq_pad;
@@ -486,7 +492,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.wave = w;
       ra.rec = wave_tensor ? rec_buf : nullptr;
       ra.rec_cnt = cnt_buf;
-      ra.rec_nsub = tensor ? plan.grid_x * 2 : 0;
+      ra.rec_nsub = tensor ? plan.rec_nsub : 0;
       ra.row_limit = n_rows;
       // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
       // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever

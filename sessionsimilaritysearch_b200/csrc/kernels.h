@@ -33,6 +33,9 @@ struct Bf16ScanPlan {
   int rec_cap;      // hit records per epilogue warp
   int n_regions;    // record sub-regions: nq_pad * grid_x * 2
   bool ts;          // query tiles resident in TMEM (A operand from TMEM) instead of shared memory
+  bool two_cta;     // cta_group::2 pairs: M=256 x N=256 MMAs, each CTA loads half of every DB tile
+  int rec_nsub;     // record sub-regions per query
+  int tile_rows;    // DB rows per tile (128, or 256 for the 2-CTA variant)
 };
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
@@ -40,6 +43,7 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream);
+unsigned long long* scan_prof_buffer();  // experiments only (SSS_SCAN_PROF)
 // select.cu — bootstrap thresholds from chunk maxima: thr[q] = just below (2k-th largest chunk max - slack)
 int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
                          float slack_mult, SelectState st, cudaStream_t stream);

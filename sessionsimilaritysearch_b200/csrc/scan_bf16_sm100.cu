@@ -105,19 +105,22 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTi
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
       : "memory");
 }
 // A operand from TMEM (lane = query row, one 32-bit column = two consecutive K elements), B from shared memory
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
+                                             uint32_t idesc = kIdesc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -134,7 +137,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -168,6 +174,8 @@ struct ScanParams {
   int rec_cap;
   int* err_flag;
   const uint4* q_bf16;   // [nq_pad, d_pad] bf16, 16-byte aligned rows (TS variant reads it directly)
+  unsigned long long* prof;  // experiments only: [0] MMA wait tempty, [1] MMA wait full, [2] MMA issue, [3] epi wait tfull, [4] epi work, [5] units
+  int dbg;               // experiments only (SSS_SCAN_DBG): 1 = read half of the accumulator columns, 2 = read all, test half
   float* cmax;           // bootstrap mode: write the max of every 32-row chunk to cmax[chunk * nq_pad + q] instead
                          // of filtering (chunk counted from row_begin)
 };
@@ -248,7 +256,7 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0) {  // whole warp, uniform: one elected lane issues (keeps descriptors in uniform registers)
       mbar_wait(qfull_bar, 0, p.err_flag, 102);
       tc_fence_after();
       uint32_t u = 0;
@@ -423,7 +431,7 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
     if (lane == 0 && my_tiles > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0; it < my_tiles && p.dbg != 5 && p.dbg != 8; ++it) {
         mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 201);
         mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.num_kb * kKBlockBytes);
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -436,31 +444,56 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0) {  // whole warp, uniform: one elected lane issues
       mbar_wait(qready_bar, 0, p.err_flag, 202);
       tc_fence_after();
       uint32_t u = 0;
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0, w_full = 0, t_issue = 0;
+      unsigned long long g0t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0t));
+      const long long cl0 = clock64();
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 203);
+        long long c0 = clock64();
+        if (p.dbg != 5 && p.dbg != 8) mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 203);
         tc_fence_after();
+        w_full += clock64() - c0;
         for (int mt = 0; mt < num_mt; ++mt, ++u) {
           const uint32_t slot = u & 1u;
-          mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 204);
+          c0 = clock64();
+          if (p.dbg != 8) mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 204);
           tc_fence_after();
+          const long long c1 = clock64();
+          w_empty += c1 - c0;
           const uint32_t d_tmem = d_base + slot * (uint32_t)kTileRows;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(mt * p.num_kb + kb) * 32u;
             const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
+            // experiments (SSS_SCAN_DBG): 3 = issue half of the MMAs, 4 = all MMAs at N=64 (half the work each)
+            const int k4_end = p.dbg == 3 ? 2 : 4;
+            const uint32_t idesc = p.dbg == 4 ? ((kIdesc & ~(0x3Fu << 17)) | ((64u >> 3) << 17)) : kIdesc;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)  // K=16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-              umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+              if (k4 < k4_end)
+                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u,
+                             idesc);
           }
           umma_commit(tfull_bar + 8 * slot);
+          t_issue += clock64() - c1;
         }
         umma_commit(empty_bar + 8 * stage);
         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+      if (p.prof != nullptr && lane == 0) {
+        atomicAdd(&p.prof[0], (unsigned long long)w_empty);
+        atomicAdd(&p.prof[1], (unsigned long long)w_full);
+        atomicAdd(&p.prof[2], (unsigned long long)t_issue);
+        atomicAdd(&p.prof[5], (unsigned long long)u);
+        unsigned long long g1t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1t));
+        atomicAdd(&p.prof[6], g1t - g0t);
+        atomicAdd(&p.prof[7], (unsigned long long)(clock64() - cl0));
       }
     }
   } else if (warp >= 4) {
@@ -507,8 +540,10 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
       HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * kRecSubCap;
       mt += 2;
       while (mt >= num_mt) { mt -= num_mt; ++it; }
+      const long long e0 = clock64();
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 205);
       tc_fence_after();
+      if (p.prof != nullptr && ew == 0 && lane == 0) atomicAdd(&p.prof[3], (unsigned long long)(clock64() - e0));
       const uint32_t taddr = d_base + lane_base + slot * (uint32_t)kTileRows;
       auto process = [&](const uint32_t (&r)[32], int c) {
         float f[32];
@@ -541,22 +576,35 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
           }
         }
       };
+      if (p.dbg == 6 || p.dbg == 8) {  // experiment: barrier handshakes only
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+        continue;
+      }
       uint32_t ra[32], rb[32];
       tmem_ld32(taddr, ra);
       tmem_ld_wait();
       tmem_ld32(taddr + 32u, rb);
       process(ra, 0);
       tmem_ld_wait();
+      if (p.dbg == 1) {  // experiment: half of the TMEM reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+        process(rb, 1);
+        continue;
+      }
       tmem_ld32(taddr + 64u, ra);
       process(rb, 1);
       tmem_ld_wait();
       tmem_ld32(taddr + 96u, rb);
-      process(ra, 2);
+      if (p.dbg != 2) process(ra, 2);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
-      process(rb, 3);
+      if (p.dbg != 2) process(rb, 3);
     }
     for (int m = 0; m < num_mt; ++m) {
       const uint32_t qidx = (uint32_t)((mt_base + m) * kTileQ + quarter * 32 + lane);
@@ -569,6 +617,271 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2-CTA variant (thread-block cluster of two CTAs on one TPC, tcgen05 cta_group::2).  One MMA covers M = 256
+// queries (128 from each CTA's shared memory) x N = 256 DB rows (128 from each CTA's shared memory): every CTA
+// loads only HALF of each DB tile, the single issuing thread (leader CTA) dispatches instructions that are
+// twice as long (128 cycles), and both tensor cores run off one instruction stream.  Each CTA keeps its own
+// queries' accumulators in its own TMEM (2 slots x 256 columns) and runs its own epilogue.
+//   full[stage]    lives in the leader; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA form)
+//   empty[stage]   one per CTA, signalled by a multicast tcgen05.commit from the leader
+//   tfull[slot]    one per CTA, multicast commit
+//   tempty[slot]   leader only, 8 arrivals: the 4 epilogue warps of the owning warpgroup in BOTH CTAs
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");  // (not .aligned: single-lane roles reach it diverged)
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc2), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                      const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = (int)(blockIdx.x >> 1);
+  const int n_pairs = (int)(gridDim.x >> 1);
+  const int nq_pad = p.total_mtiles * kTileQ;
+
+  // m-tiles of this CTA: group base g0, unit j -> m-tile g0 + 2 * j + rank
+  const int g0 = blockIdx.y * 2 * p.num_mt;
+  const int mt_in_group = min(2 * p.num_mt, p.total_mtiles - g0);
+  const int num_j = (mt_in_group + 1) / 2;                   // MMA units per DB tile (same in both CTAs)
+  const int n_tiles = (int)p.n_tiles;                        // 256-row tiles in this wave
+  const int my_tiles = pair < n_tiles ? (n_tiles - 1 - pair) / n_pairs + 1 : 0;
+
+  const uint32_t q_smem = smem_base;
+  const uint32_t db_smem = q_smem + (uint32_t)(p.num_mt * p.num_kb) * kKBlockBytes;
+  const uint32_t bar_base = db_smem + (uint32_t)(p.num_stages * p.num_kb) * kKBlockBytes;
+  const uint32_t full_bar = bar_base;                         // [kMaxStages] (leader's are used)
+  const uint32_t empty_bar = bar_base + 8 * kMaxStages;       // [kMaxStages]
+  const uint32_t tfull_bar = bar_base + 16 * kMaxStages;      // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                 // [2] (leader's are used)
+  const uint32_t qfull_bar = tempty_bar + 16;                 // [1]
+  const uint32_t tmem_ptr_addr = qfull_bar + 8;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_db);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 8);
+    }
+    mbar_init(qfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  // resident query tiles of this CTA; the leader may only start once BOTH CTAs hold theirs
+  if (warp == 0 && lane == 0 && my_tiles > 0) {
+    mbar_expect_tx(qfull_bar, (uint32_t)(num_j * p.num_kb) * kKBlockBytes);
+    for (int j = 0; j < num_j; ++j)
+      for (int kb = 0; kb < p.num_kb; ++kb)
+        tma_load_2d(q_smem + (uint32_t)(j * p.num_kb + kb) * kKBlockBytes, &tmap_q, qfull_bar, kb * 64,
+                    (g0 + 2 * j + (int)rank) * kTileQ);
+    mbar_wait(qfull_bar, 0, p.err_flag, 302);
+  }
+  cluster_sync_all();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own half of every DB tile =====================
+    if (lane == 0 && my_tiles > 0) {
+      const uint32_t leader_full = map_to_cta(full_bar, 0);  // the leader's barrier, shared::cluster address
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 301);
+        if (leader) mbar_expect_tx(full_bar + 8 * stage, 2u * (uint32_t)p.num_kb * kKBlockBytes);
+        const int tile = pair + it * n_pairs;
+        const int row = (int)p.row_begin + tile * 256 + (int)rank * kTileRows;
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d_2sm(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes, &tmap_db,
+                          leader_full + 8 * stage, kb * 64, row);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && my_tiles > 0) {  // whole warp, uniform: one elected lane issues
+      tc_fence_after();
+      uint32_t u = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 303);
+        tc_fence_after();
+        for (int j = 0; j < num_j; ++j, ++u) {
+          const uint32_t slot = u & 1u;
+          mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 304);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * 256u;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const uint64_t adesc = umma_desc_sw128(q_smem + (uint32_t)(j * p.num_kb + kb) * kKBlockBytes);
+            const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(tfull_bar + 8 * slot);
+        }
+        umma_commit_2cta(empty_bar + 8 * stage);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): fused top-k filter over 256 columns per unit ==========
+    const int ew = warp - 4;
+    const int wg = ew >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t leader_tempty = map_to_cta(tempty_bar, 0);
+    uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+    const uint32_t sub_stride = (uint32_t)n_pairs * 2u;
+    const uint32_t my_sub = (uint32_t)pair * 2u + (uint32_t)wg;
+    const int total_units = my_tiles * num_j;
+    int it = 0, j = wg;
+    while (j >= num_j) { j -= num_j; ++it; }
+    for (int u = wg; u < total_units; u += 2) {
+      const uint32_t slot = (uint32_t)wg;
+      const uint32_t ph = (uint32_t)((u >> 1) & 1);
+      const int tile = pair + it * n_pairs;
+      const int cur_j = j;
+      const uint32_t qidx = (uint32_t)((g0 + 2 * j + (int)rank) * kTileQ + quarter * 32 + lane);
+      const bool q_ok = qidx < (uint32_t)nq_pad;
+      const float thr = q_ok ? p.st.thr[qidx] : INFINITY;
+      const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * 256);
+      HitRecord* myrec = p.rec + ((size_t)(q_ok ? qidx : 0u) * sub_stride + my_sub) * kRecSubCap;
+      j += 2;
+      while (j >= num_j) { j -= num_j; ++it; }
+      mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 305);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + slot * 256u;
+      auto process = [&](const uint32_t (&r)[32], int c) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+        float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]);
+        float m2 = max3(f[6], f[7], f[8]), m3 = max3(f[9], f[10], f[11]);
+        m0 = max3(m0, f[12], f[13]); m1 = max3(m1, f[14], f[15]);
+        m2 = max3(m2, f[16], f[17]); m3 = max3(m3, f[18], f[19]);
+        m0 = max3(m0, f[20], f[21]); m1 = max3(m1, f[22], f[23]);
+        m2 = max3(m2, f[24], f[25]); m3 = max3(m3, f[26], f[27]);
+        m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
+        const float mx = fmaxf(max3(m0, m1, m2), m3);
+        if (p.cmax != nullptr) {
+          if (q_ok) {
+            const uint32_t chunk = (row_tile - (uint32_t)p.row_begin) / 32u + (uint32_t)c;
+            p.cmax[(size_t)chunk * (size_t)nq_pad + qidx] = mx;
+          }
+          return;
+        }
+        const bool hit = mx > thr;
+        if (__any_sync(0xffffffffu, hit)) {
+          if (hit) {
+            const uint32_t idx = cur_j == 0 ? rc0 : cur_j == 1 ? rc1 : cur_j == 2 ? rc2 : rc3;
+            if (idx < (uint32_t)kRecSubCap) {
+              uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
+              dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[1 + i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+            rc0 += cur_j == 0; rc1 += cur_j == 1; rc2 += cur_j == 2; rc3 += cur_j == 3;
+          }
+        }
+      };
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld32(taddr + (uint32_t)((c + 1) * 32), rb);
+        process(ra, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) {
+          tmem_ld32(taddr + (uint32_t)((c + 2) * 32), ra);
+        } else {  // all eight chunks have left TMEM: hand the slot back to the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar + 8 * slot);
+            else mbar_arrive_remote(leader_tempty + 8 * slot);
+          }
+        }
+        process(rb, c + 1);
+        if (c + 2 < 8) tmem_ld_wait();
+      }
+    }
+    for (int m = 0; m < num_j; ++m) {
+      const uint32_t qidx = (uint32_t)((g0 + 2 * m + (int)rank) * kTileQ + quarter * 32 + lane);
+      if (qidx < (uint32_t)nq_pad)
+        p.rec_cnt[(size_t)qidx * sub_stride + my_sub] = m == 0 ? rc0 : m == 1 ? rc1 : m == 2 ? rc2 : rc3;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -616,7 +929,36 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   plan->grid_x = num_sms / plan->grid_y;
   if (plan->grid_x < 1) plan->grid_x = 1;
   const char* force_ss = getenv("SSS_SCAN_SS");
+  const char* variant = getenv("SSS_SCAN_VARIANT");  // "2cta" (default), "ts", "ss"
   plan->ts = !(force_ss && force_ss[0] == '1');  // A operand from TMEM unless the SS form is forced
+  plan->two_cta = !(variant && (variant[0] == 't' || variant[0] == 's')) && !(force_ss && force_ss[0] == '1');
+  if (variant && variant[0] == 's') plan->ts = false;
+  if (plan->two_cta) {
+    // pairs of CTAs: every pair holds up to 8 m-tiles (4 per CTA) and walks 256-row DB tiles
+    plan->ts = false;
+    plan->num_kb = d_pad / 64;
+    plan->total_mtiles = total_mtiles;
+    plan->grid_y = (total_mtiles + 7) / 8;
+    const int per_group = (total_mtiles + plan->grid_y - 1) / plan->grid_y;  // m-tiles per pair
+    plan->num_mt = (per_group + 1) / 2;                                      // per CTA
+    int pairs = (num_sms / 2) / plan->grid_y;
+    if (pairs < 1) pairs = 1;
+    plan->grid_x = 2 * pairs;
+    const int q_bytes2 = plan->num_mt * plan->num_kb * kKBlockBytes;
+    const int stage_bytes2 = plan->num_kb * kKBlockBytes;
+    int stages2 = (227 * 1024 - 1024 - kBarrierBytes - q_bytes2) / stage_bytes2;
+    if (stages2 > kMaxStages) stages2 = kMaxStages;
+    if (stages2 > max_stages) stages2 = max_stages;
+    SSS_REQUIRE(stages2 >= 2, "not enough shared memory for the DB tile ring");
+    plan->num_stages = stages2;
+    plan->smem_bytes = 1024 + q_bytes2 + stages2 * stage_bytes2 + kBarrierBytes;
+    plan->rec_cap = kRecSubCap;
+    plan->rec_nsub = pairs * 2;
+    plan->n_regions = (int)nq_pad * plan->rec_nsub;
+    plan->tile_rows = 256;
+    return 0;
+  }
+  plan->tile_rows = kTileRows;
   const int q_bytes = plan->ts ? 0 : plan->num_mt * plan->num_kb * kKBlockBytes;
   const int stage_bytes = plan->num_kb * kKBlockBytes;
   const int avail = 227 * 1024 - 1024 - kBarrierBytes - q_bytes;
@@ -627,22 +969,26 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   plan->num_stages = stages;
   plan->smem_bytes = 1024 + q_bytes + stages * stage_bytes + kBarrierBytes;
   plan->rec_cap = kRecSubCap;
-  plan->n_regions = (int)nq_pad * plan->grid_x * 2;
+  plan->rec_nsub = plan->grid_x * 2;
+  plan->n_regions = (int)nq_pad * plan->rec_nsub;
   return 0;
 }
+
+static unsigned long long* g_scan_prof = nullptr;
+unsigned long long* scan_prof_buffer() { return g_scan_prof; }
 
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream) {
-  SSS_REQUIRE(cmax == nullptr || plan.ts, "chunk-max bootstrap needs the TS scan variant");
-  SSS_REQUIRE(row_begin % kTileRows == 0, "scan wave must start on a 128-row boundary");
+  SSS_REQUIRE(cmax == nullptr || plan.ts || plan.two_cta, "chunk-max bootstrap needs the TS or 2-CTA scan variant");
+  SSS_REQUIRE(row_begin % plan.tile_rows == 0, "scan wave must start on a tile boundary");
   ScanParams p;
   p.num_kb = plan.num_kb;
   p.num_mt = plan.num_mt;
   p.num_stages = plan.num_stages;
   p.total_mtiles = plan.total_mtiles;
   p.row_begin = row_begin;
-  p.n_tiles = (row_end - row_begin + kTileRows - 1) / kTileRows;
+  p.n_tiles = (row_end - row_begin + plan.tile_rows - 1) / plan.tile_rows;
   p.st = st;
   p.rec = rec;
   p.rec_cnt = rec_cnt;
@@ -650,16 +996,45 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.err_flag = err_flag;
   p.q_bf16 = (const uint4*)q_bf16;
   p.cmax = cmax;
+  {
+    const char* dbg = getenv("SSS_SCAN_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+    p.prof = nullptr;
+    if (getenv("SSS_SCAN_PROF")) {
+      if (!g_scan_prof) {
+        SSS_CUDA_OK(cudaMalloc((void**)&g_scan_prof, 8 * sizeof(unsigned long long)));
+        SSS_CUDA_OK(cudaMemset(g_scan_prof, 0, 8 * sizeof(unsigned long long)));
+      }
+      p.prof = g_scan_prof;
+    }
+  }
   if (p.n_tiles <= 0) return 0;
   static int smem_set = 0;
   if (smem_set < plan.smem_bytes) {
     SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
     SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      plan.smem_bytes));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     plan.smem_bytes));
     smem_set = plan.smem_bytes;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  if (plan.ts)
+  if (plan.two_cta) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel, *(const CUtensorMap*)tmap_q,
+                                   *(const CUtensorMap*)tmap_db, p));
+  } else if (plan.ts)
     scan_bf16_ts_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_db, p);
   else
     scan_bf16_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_q,

@@ -516,35 +516,63 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
 // can only matter if its tensor-core score is >= T - 2 * margin: thr = the float just below that.
 __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq_pad,
                                                             int k, int chunk_gap, float slack_mult, SelectState st) {
-  extern __shared__ uint64_t bs_keys[];  // [P]
+  extern __shared__ uint32_t bs_keys[];  // [n_chunks]
+  __shared__ uint32_t hist[256];
+  __shared__ int s_bin, s_above;
   const int q = blockIdx.x;
-  int P = 2;
-  while (P < n_chunks) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += blockDim.x)
-    bs_keys[i] = i < n_chunks ? (((uint64_t)score_key(cmax[(size_t)i * nq_pad + q]) << 32) | (uint64_t)(uint32_t)i) : 0ull;
-  __syncthreads();
-  bitonic_desc(bs_keys, P);
-  if (threadIdx.x == 0) {
-    // of the `need` largest chunks, taken in index order, every gap-th one is >= gap chunks from the previous pick
-    const int need = (k - 1) * chunk_gap + 1;
-    if (need <= n_chunks) {
-      const float T = key_score((uint32_t)(bs_keys[need - 1] >> 32));
-      st.thr[q] = nextafterf(T - slack_mult * st.margin[q], -INFINITY);
+  const int tid = threadIdx.x, lane = tid & 31;
+  // of the `need` largest chunks, taken in index order, every gap-th one is >= gap chunks from the previous pick
+  const int need = (k - 1) * chunk_gap + 1;
+  if (need > n_chunks) return;
+  for (int i = tid; i < n_chunks; i += blockDim.x) bs_keys[i] = score_key(cmax[(size_t)i * nq_pad + q]);
+  // radix select (4 x 8 bits) of the need-th largest key
+  uint32_t prefix = 0u, mask = 0u;
+  int want = need;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n_chunks; i += blockDim.x) {
+      const uint32_t key = bs_keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
     }
+    __syncthreads();
+    if (tid < 32) {  // lane l owns bins [8l, 8l + 8); find the bin where the count from the top reaches `want`
+      int mine = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) mine += (int)hist[lane * 8 + b];
+      int above = mine;  // inclusive suffix sum over lanes >= l
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, above, o);
+        if (lane + o < 32) above += t;
+      }
+      const int strictly_above = above - mine;  // counts in higher lanes
+      if (strictly_above < want && above >= want) {
+        int acc = strictly_above;
+        for (int b = 7; b >= 0; --b) {
+          const int c = (int)hist[lane * 8 + b];
+          if (acc + c >= want) {
+            s_bin = lane * 8 + b;
+            s_above = acc;
+            break;
+          }
+          acc += c;
+        }
+      }
+    }
+    __syncthreads();
+    want -= s_above;
+    prefix |= (uint32_t)s_bin << shift;
+    mask |= 0xFFu << shift;
+    __syncthreads();
   }
+  if (tid == 0) st.thr[q] = nextafterf(key_score(prefix) - slack_mult * st.margin[q], -INFINITY);
 }
 
 int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
                          float slack_mult, SelectState st, cudaStream_t stream) {
-  int P = 2;
-  while (P < n_chunks) P <<= 1;
-  SSS_REQUIRE(P <= 8192, "bootstrap region too large");
-  static bool attr = false;
-  if (!attr) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(bootstrap_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    attr = true;
-  }
-  bootstrap_thr_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(cmax, n_chunks, nq_pad, k, chunk_gap, slack_mult, st);
+  SSS_REQUIRE(n_chunks <= 8192, "bootstrap region too large");
+  bootstrap_thr_kernel<<<(unsigned)nq, 256, (size_t)n_chunks * 4, stream>>>(cmax, n_chunks, nq_pad, k, chunk_gap,
+                                                                           slack_mult, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
