@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -171,6 +171,42 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
+
+
+def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
+    """config 5, encoder leg: the reference's model shape (768 -> 3 x 800 -> 3168 -> 1600, pretrain_filtered_amazon.py:
+    262-287) on synthetic Amazon-filtered-shaped sessions, eval batch size 200 (test_amazon_filterd.py:488); features
+    are precomputed (the private text model is outside the CUDA scope).  CPU figure: the encoder oracle, one batch."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import encoder_common as ec
+    import sessionsimilaritysearch_b200 as sss
+    from sessionsimilaritysearch_b200 import graph, sessions, synth
+    in_dim, hidden, n_layers, out_dim, msl = 768, 800, 3, 1600, 20
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 11)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl,
+                             device=device)
+    _, graphs = ec.make_graphs(n_sessions, in_dim, 17, sessions.sequence_to_graph)
+    batches = [graph.collate(graphs[i:i + batch]).to("cuda:%d" % device) for i in range(0, n_sessions, batch)]
+    for b in batches[:2]:
+        enc(b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in batches:
+        enc(b)
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"encoder_sessions_per_s": n_sessions / (e0.elapsed_time(e1) * 1e-3),
+           "encoder_nodes_per_batch": int(batches[0]['query'].x.shape[0] + batches[0]['product'].x.shape[0])}
+    if not no_cpu:
+        from oracle import encoder_oracle as eo
+        cb = eo.batch_from_pyg(graph.collate(graphs[:batch]))
+        t0 = time.perf_counter()
+        eo.encoder_forward(P, cb, n_layers)
+        out["encoder_cpu_sessions_per_s"] = batch / (time.perf_counter() - t0)
+        out["encoder_cpu_threads"] = torch.get_num_threads()
+    return out
 
 
 def workload_config(a):
@@ -285,6 +321,7 @@ def main():
     kernels_per_step = inner.stats()["kernels"] + (1 if world > 1 else 0)
     waves = inner.stats()["waves"]
     reruns = inner.stats()["reruns"]
+    overflow_reason = inner.stats()["overflow_reason"]
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
@@ -323,6 +360,12 @@ def main():
         except RuntimeError as e:
             extra["nq1_ms"] = "error: %s" % e
 
+    if not a.no_extra and world == 1:
+        try:
+            extra.update(encoder_bench(local_rank, no_cpu=a.no_cpu_baseline))
+        except Exception as e:  # the headline number must not depend on the encoder leg
+            extra["encoder_error"] = str(e)[:200]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -333,12 +376,28 @@ def main():
     flops_per_step = 2.0 * a.nq * rows_local * a.d
     scan_s = scan_ns[0] * 1e-9 / a.steps
     tensor_mode = a.mode in ("exact", "bf16")
-    if tensor_mode:
+    ridge = float(peaks.get("bf16_tflops_sustained", 1400.0)) * 1e12 / (float(peaks.get("hbm_gbs", 6650.0)) * 1e9)
+    if tensor_mode and a.nq < ridge:
+        # fewer resident queries than the ridge (flop per DB byte): the pass is bound by the DB stream
+        d_pad = (a.d + 63) // 64 * 64
+        nq_pad = (a.nq + 127) // 128 * 128
+        bytes_per_step = rows_local * d_pad * 2 + nq_pad * d_pad * 2
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_per_step / scan_s / 1e9 if scan_s > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
+                    "kernel": "scan_bf16_2cta_kernel", "launches_per_step": scan_ns[1] / a.steps,
+                    "kernel_ms_per_step": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / ms_step,
+                    "algorithmic": "rows*d_pad*2 + nq_pad*d_pad*2 B = %.3e per step (nq %d < ridge %.0f)"
+                                   % (bytes_per_step, a.nq, ridge),
+                    "whole_step_gbs": bytes_per_step / (ms_step * 1e-3) / 1e9}
+    elif tensor_mode:
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         achieved = flops_per_step / scan_s / 1e12 if scan_s > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind + " sustained bf16",
-                    "kernel": "scan_bf16_kernel", "launches_per_step": scan_ns[1] / a.steps,
+                    "kernel": {"ts": "scan_bf16_ts_kernel", "ss": "scan_bf16_kernel"}.get(
+                        os.environ.get("SSS_SCAN_VARIANT", ""), "scan_bf16_2cta_kernel"), "launches_per_step": scan_ns[1] / a.steps,
                     "kernel_ms_per_step": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / ms_step,
                     "algorithmic": "2*nq*rows*d flop = %.3e per step" % flops_per_step}
     else:
@@ -348,7 +407,7 @@ def main():
                     "traffic": None, "peak_kind": "nominal fp32 CUDA-core FMA peak (no tensor path in fp32 mode)",
                     "kernel": "scan_fp32_kernel"}
     tfile = os.path.join(ROOT, "profiles", "scan_traffic_bytes_per_step.json")
-    if os.path.exists(tfile):
+    if os.path.exists(tfile) and roofline["bound"] == "tensor" and a.rows == 10000000 and a.nq == 1000:
         try:
             roofline["traffic"] = json.load(open(tfile)).get("bytes_per_step")
         except Exception:
@@ -382,7 +441,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "waves_per_step": waves, "overflow_reruns": reruns, "refine_volumes_last_step": refine_stats,
+        "waves_per_step": waves, "overflow_reruns": reruns, "overflow_reason": overflow_reason, "refine_volumes_last_step": refine_stats,
         "extra": extra,
     }
     print(json.dumps(out))

@@ -93,7 +93,9 @@ int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mod
 /* Counters of the last search on this handle.  what: 0 = kernels launched, 1 = scan waves,
  * 2 = overflow reruns, 3 = scan-kernel device time in ns, 4 = scan-kernel launches (3 and 4 need
  * sss_index_set_profiling(ix, 1): CUDA events are then recorded around every scan launch on the caller's
- * stream). */
+ * stream), 5..23 = refine volumes / phase cycles / scan role counters of profiling builds, 24 = bit mask of
+ * what overflowed when the last search had to be redone with the safe schedule (1 record sub-region,
+ * 2 records per query, 4 candidate list, 8 new candidates, 16 session table, 32 re-score list). */
 int64_t sss_index_stat(const sss_index_t* ix, int what);
 int sss_index_set_profiling(sss_index_t* ix, int on);
 

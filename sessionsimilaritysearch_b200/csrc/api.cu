@@ -172,7 +172,7 @@ struct sss_index {
   int64_t* seg_off = nullptr;  // device
   int32_t* row_seg = nullptr;  // device
   Workspace ws;
-  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0;
+  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0, stat_overflow_reason = 0;
   // optional scan-kernel timing (CUDA events on the launching stream around every scan launch)
   bool profile = false;
   std::vector<cudaEvent_t> ev;
@@ -240,6 +240,7 @@ extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
     case 0: return ix->stat_kernels;
     case 1: return ix->stat_waves;
     case 2: return ix->stat_reruns;
+    case 24: return ix->stat_overflow_reason;  // bit mask of what overflowed in the last rerun (select.cu)
     case 3: return (int64_t)(ix->scan_us * 1000.0);  // scan-kernel time of the last search, ns (profiling on)
     case 4: return ix->scan_launches;
     case 5: return (int64_t)ix->dbg_host[0];  // candidates entering refine (profiling on)
@@ -341,13 +342,24 @@ namespace sss {
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
 static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups = false,
-                                       int64_t bootstrap_rows = 0) {
+                                       int64_t bootstrap_rows = 0, bool few_queries = false) {
   std::vector<int64_t> ends;
-  if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): start at half of it
-    int64_t e = bootstrap_rows / 2;
+  if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): re-scan those rows first
+    // Measured at 10M rows x 1000 queries (profiles/r01_wave_schedule.md): refine cost follows the candidate volume,
+    // not the wave count, so longer waves buy nothing there, and from x3.5 on a (query, pair, warpgroup) record
+    // sub-region can exceed its 16 records.  With a single m-tile the launch count dominates and the 1-CTA scan has
+    // twice the sub-regions per query: x3.
+    const char* g = getenv("SSS_WAVE_GROWTH");  // tuning: growth factor x10
+    const char* f = getenv("SSS_WAVE_FIRST");   // tuning: rows of the first wave
+    const int64_t growth10 = g ? std::max<int64_t>(11, atoll(g)) : (few_queries ? 30 : 20);
+    int64_t e = f ? std::max<int64_t>(256, atoll(f) / 256 * 256) : bootstrap_rows;
+    e = std::min(e, n_rows);
     ends.push_back(e);
     while (e < n_rows) {
-      e = std::min(n_rows, 2 * e);
+      int64_t nx = (e * growth10 / 10 + 255) / 256 * 256;
+      // do not leave a short tail wave: fold anything below a quarter wave into this one
+      if (n_rows - nx < (nx - e) / 4) nx = n_rows;
+      e = std::min(n_rows, nx);
       ends.push_back(e);
     }
     return ends;
@@ -466,7 +478,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, b.nq, nq_pad, b.k, chunk_gap, 2.0f, state, st)) return 1;
       ix->stat_kernels += 2;
     }
-    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, grouped, bootstrap ? kBootRows : 0);
+    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, grouped, bootstrap ? kBootRows : 0, tensor && plan.total_mtiles == 1);
     int64_t begin = 0;
     uint32_t wave_id = 0;
     bool prev_tensor = false;
@@ -555,6 +567,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     // cannot overflow by construction
     SSS_REQUIRE(attempt == 0, "candidate overflow persisted in the safe wave schedule (internal error)");
     ix->stat_reruns += 1;
+    ix->stat_overflow_reason = flags[0];
   }
   return 0;
 }

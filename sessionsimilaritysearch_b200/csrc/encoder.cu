@@ -329,23 +329,62 @@ struct sss_encoder {
   std::map<std::string, float*> params;
   std::map<std::string, int64_t> numel;
   cublasHandle_t blas = nullptr;
-  // workspace
-  std::vector<void*> pool;
+  // Workspace arena: slabs are bump-allocated per forward call and kept across calls (cudaMalloc/cudaFree per
+  // buffer cost more than the whole forward).  A call that needed more than one slab is followed by one
+  // consolidation at the start of the next call; `done` orders reuse across streams.
+  std::vector<std::pair<char*, size_t>> slabs;
+  size_t used = 0;        // bytes taken from the last slab
+  size_t requested = 0;   // bytes requested by the current / last call
+  cudaEvent_t done = nullptr;
+  bool done_recorded = false;
   ~sss_encoder() {}
 };
 
 namespace {
+constexpr size_t kSlabAlign = 256, kMinSlab = (size_t)32 << 20;
+int ws_begin(sss_encoder* e, cudaStream_t st) {
+  if (!e->done) SSS_CUDA_OK(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
+  if (e->slabs.size() > 1) {  // the last call outgrew its slab: one slab of the full size from now on
+    if (e->done_recorded) SSS_CUDA_OK(cudaEventSynchronize(e->done));
+    for (auto& s : e->slabs) cudaFree(s.first);
+    e->slabs.clear();
+    const size_t want = e->requested + e->requested / 4;
+    char* v = nullptr;
+    SSS_CUDA_OK(cudaMalloc((void**)&v, want));
+    e->slabs.emplace_back(v, want);
+  }
+  if (e->done_recorded) SSS_CUDA_OK(cudaStreamWaitEvent(st, e->done, 0));
+  e->used = 0;
+  e->requested = 0;
+  return 0;
+}
+int ws_end(sss_encoder* e, cudaStream_t st) {
+  SSS_CUDA_OK(cudaEventRecord(e->done, st));
+  e->done_recorded = true;
+  return 0;
+}
 template <typename T>
 int ws_alloc(sss_encoder* e, T** p, size_t count) {
-  void* v = nullptr;
-  SSS_CUDA_OK(cudaMalloc(&v, (count > 0 ? count : 1) * sizeof(T)));
-  e->pool.push_back(v);
-  *p = (T*)v;
+  size_t bytes = ((count > 0 ? count : 1) * sizeof(T) + kSlabAlign - 1) / kSlabAlign * kSlabAlign;
+  e->requested += bytes;
+  if (e->slabs.empty() || e->used + bytes > e->slabs.back().second) {
+    const size_t want = bytes > kMinSlab ? bytes : kMinSlab;
+    char* v = nullptr;
+    SSS_CUDA_OK(cudaMalloc((void**)&v, want));
+    e->slabs.emplace_back(v, want);
+    e->used = 0;
+  }
+  *p = (T*)(e->slabs.back().first + e->used);
+  e->used += bytes;
   return 0;
 }
 void ws_release(sss_encoder* e) {
-  for (void* v : e->pool) cudaFree(v);
-  e->pool.clear();
+  if (e->done_recorded) cudaEventSynchronize(e->done);
+  for (auto& s : e->slabs) cudaFree(s.first);
+  e->slabs.clear();
+  if (e->done) cudaEventDestroy(e->done);
+  e->done = nullptr;
+  e->done_recorded = false;
 }
 struct Csr {
   int* rowptr = nullptr;
@@ -470,7 +509,7 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
   } restore{prev, e};
   cudaStream_t st = (cudaStream_t)stream;
   SSS_REQUIRE(g_cublas.set_stream(e->blas, st) == 0, "cublasSetStream failed");
-  ws_release(e);  // buffers of the previous call (its stream work was synchronised below)
+  if (ws_begin(e, st)) return 1;
 
   // ---- workspace
   float *Zq, *Zp, *Sq, *Sp, *as_q, *ad_q, *as_p, *ad_p, *Gp, *Agg, *gi, *gh, *uq_lin, *up_lin, *U, *coarse, *Aatt, *Bc, *att;
@@ -566,8 +605,7 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
   pool_att_kernel<<<NT, 256, 0, st>>>(Aatt, bn, Bc, node_graph, wa, OUT, att);
   graph_mean_kernel<<<B, 256, 0, st>>>(U, OUT, ranges, att, out);
   SSS_CUDA_OK(cudaGetLastError());
-  SSS_CUDA_OK(cudaStreamSynchronize(st));  // workspace is recycled by the next call
-  return 0;
+  return ws_end(e, st);
 }
 
 extern "C" int sss_binarize_head(const float* x, const float* W, const float* b, int64_t n, int in_dim, int out_dim,

@@ -647,7 +647,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the slot hand-off orders TMEM reads through the tcgen05 fences, and a
+  // cluster-scope release compiles to MEMBAR.ALL.GPU in front of every arrive (1-2 us under a saturated HBM stream)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -932,6 +934,9 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   const char* variant = getenv("SSS_SCAN_VARIANT");  // "2cta" (default), "ts", "ss"
   plan->ts = !(force_ss && force_ss[0] == '1');  // A operand from TMEM unless the SS form is forced
   plan->two_cta = !(variant && (variant[0] == 't' || variant[0] == 's')) && !(force_ss && force_ss[0] == '1');
+  // one m-tile (<= 128 queries) is the DB-stream-bound regime: independent 1-CTA tiles with the queries in TMEM
+  // reach 0.86 of the HBM copy bandwidth, the pair kernel (half of every MMA is padding there) 0.77
+  if (total_mtiles == 1 && !(variant && variant[0] == '2')) plan->two_cta = false;
   if (variant && variant[0] == 's') plan->ts = false;
   if (plan->two_cta) {
     // pairs of CTAs: every pair holds up to 8 m-tiles (4 per CTA) and walks 256-row DB tiles

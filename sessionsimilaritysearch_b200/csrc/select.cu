@@ -83,21 +83,21 @@ struct RefineCfg {
   static constexpr int kNc = NC;                 // max new candidates per query and wave
   static constexpr int kSurv = SURV;             // max rows re-scored per query and wave
   static constexpr int kKmax = KMAX;             // max k (retained entries)
-  static constexpr int kRsw = RSW;               // re-scoring warps
-  static constexpr int kKc = KC;                 // tile columns
+  static constexpr int kRsw = RSW;               // (unused since the per-lane row walk)
+  static constexpr int kKc = KC;                 // query staging is zero-padded to a multiple of this
   static constexpr int kThreads = THREADS;
   static constexpr int kRmax = RMAX;             // max hit records per query and wave
   static constexpr bool kLast = LAST;            // nobody behind us: too-large inputs are an overflow
   static constexpr int kMaxSub = 512;            // max record sub-regions per query (2 * grid_x)
-  // scratch = [recptr | subpre | tiles], reused as the gather/sort array A[kSlots] once the passes are done
+  // scratch = [recptr | subpre], reused as the gather/sort array A[kSlots] once the passes are done
   __host__ __device__ static constexpr size_t scratch_bytes() {
-    size_t s = (size_t)RMAX * 4 + (size_t)(kMaxSub + 1) * 4 + 4 + sizeof(float) * (size_t)RSW * 32 * (KC + 1);
+    size_t s = (size_t)RMAX * 4 + (size_t)(kMaxSub + 1) * 4 + 8;
     size_t a = (size_t)kSlots * 8;
-    return (s > a ? s : a) + 8;
+    return ((s > a ? s : a) + 15) / 16 * 16;
   }
   static constexpr size_t smem_bytes(int d_round, bool rescore) {
     return scratch_bytes() + 4096 + (size_t)kSlots * 8 + (size_t)NC * 8 + 16 + (size_t)NC * 2 + (size_t)SURV * 2 +
-           (size_t)KMAX * 2 + 8 + sizeof(float) * (rescore ? d_round : 0);
+           (size_t)KMAX * 2 + 8 + 16 + sizeof(float) * (rescore ? d_round : 0);
   }
 };
 
@@ -109,7 +109,6 @@ struct RefineSmem {
   uint64_t* tmp;        // [512] rank-sort staging
   uint32_t* recptr;     // [RMAX] global record index
   uint32_t* subpre;     // [kMaxSub + 1]
-  float* tiles;         // [RSW][32][KC+1]
   uint32_t* owner;      // [slots] session + 1
   uint32_t* best;       // [slots] max key
   uint32_t* ent_key;    // [NC] compacted new candidates
@@ -123,7 +122,6 @@ struct RefineSmem {
     A = reinterpret_cast<uint64_t*>(p);
     recptr = reinterpret_cast<uint32_t*>(p);
     subpre = recptr + C::kRmax;
-    tiles = reinterpret_cast<float*>(subpre + C::kMaxSub + 2);
     tmp = reinterpret_cast<uint64_t*>(p + C::scratch_bytes());
     unsigned char* rest = p + C::scratch_bytes() + 4096;
     owner = reinterpret_cast<uint32_t*>(rest);
@@ -134,7 +132,7 @@ struct RefineSmem {
     ent_slot = reinterpret_cast<uint16_t*>(ctr + 4);
     surv = ent_slot + C::kNc;
     ret_slot = surv + C::kSurv;
-    qs = reinterpret_cast<float*>(ret_slot + C::kKmax + ((C::kNc + C::kSurv + C::kKmax) & 1));
+    qs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ret_slot + C::kKmax) + 15) & ~(uintptr_t)15);  // float4 reads
   }
 };
 
@@ -208,7 +206,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         if (s0 + lane < nsub) {
           cnt = a.rec_cnt[sub0 + s0 + lane];
           if (cnt > (uint32_t)kRecSubCap) {
-            *st.overflow = 1;
+            atomicOr(st.overflow, 1);   // reason codes: sss_index_stat(ix, 24)
             cnt = kRecSubCap;
           }
         }
@@ -227,7 +225,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     if (R == 0) return RF_DONE;  // nothing new since the last refine
     if (R > C::kRmax) {
       if (!C::kLast) return RF_SKIP;
-      if (tid == 0) *st.overflow = 1;
+      if (tid == 0) atomicOr(st.overflow, 2);
     }
     const int Rc = R < C::kRmax ? R : C::kRmax;
     for (int s = tid; s < nsub; s += C::kThreads) {
@@ -236,8 +234,8 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         sm.recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
     }
     __syncthreads();
-    // a warp takes four records per round: four independent 128-byte loads in flight, lane = score index
-    constexpr int RU = 4;
+    // a warp takes eight records per round: eight independent 128-byte loads in flight, lane = score index
+    constexpr int RU = 8;
     for (int r0 = warp * RU; r0 < Rc; r0 += NW * RU) {
       float v[RU];
       uint32_t row[RU];
@@ -260,7 +258,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   } else {
     const uint32_t c = st.cnt[q];
     const int n = c > (uint32_t)st.cap ? st.cap : (int)c;
-    if (c > (uint32_t)st.cap && tid == 0) *st.overflow = 1;
+    if (c > (uint32_t)st.cap && tid == 0) atomicOr(st.overflow, 4);
     if (n == nr) return RF_DONE;  // nothing new since the last refine
     if (n - nr > C::kNc) {
       if (!C::kLast) return RF_SKIP;
@@ -288,7 +286,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   int n_ent = sm.ctr[0];
   if (n_ent > C::kNc) {
     if (!C::kLast) return RF_SKIP;
-    if (tid == 0) *st.overflow = 1;
+    if (tid == 0) atomicOr(st.overflow, 8);
     n_ent = C::kNc;
   }
 
@@ -317,7 +315,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     const int uniq = sm.ctr[3];
     if ((uniq & 0x40000000) != 0 || (uniq & 0x3FFFFFFF) > C::kSlots * 3 / 4) {
       if (!C::kLast) return RF_SKIP;
-      if ((uniq & 0x40000000) != 0 && tid == 0) *st.overflow = 1;  // table full: candidates were dropped
+      if ((uniq & 0x40000000) != 0 && tid == 0) atomicOr(st.overflow, 16);  // table full: candidates were dropped
     }
   }
 
@@ -338,7 +336,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     int nsurv = sm.ctr[1];
     if (nsurv > C::kSurv) {
       if (!C::kLast) return RF_SKIP;
-      if (tid == 0) *st.overflow = 1;
+      if (tid == 0) atomicOr(st.overflow, 32);
       nsurv = C::kSurv;
     }
     // final keys only from here on: retained entries keep theirs, survivors get exact ones
@@ -346,68 +344,57 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     __syncthreads();
     for (int i = tid; i < nr; i += C::kThreads) atomicMax(&sm.best[sm.ret_slot[i]], cand_key(g[i]));
     RF_PHASE(4);  // survivors + reset
-    // ---- D. exact fixed-order re-scoring of the survivors
-    if (warp < C::kRsw) {
-      constexpr int LPR = C::kKc / 4;   // lanes per row segment (float4 each)
-      constexpr int RPI = 32 / LPR;     // rows per load instruction
-      constexpr int NL = 32 / RPI;      // load instructions per tile
-      float* tile = sm.tiles + (size_t)warp * 32 * (C::kKc + 1);
-      const int rsub = lane / LPR, c4 = lane % LPR;
-      const bool vec_ok = (a.d & 3) == 0;
-      for (int base = warp * 32; base < nsurv; base += C::kRsw * 32) {
-        const int li = base + lane;
-        const bool live = li < nsurv;
-        const int ei = live ? (int)sm.surv[li] : 0;
-        const uint32_t my_row = live ? sm.ent_row[ei] : 0u;
-        const float* rowp[NL];
+    // ---- D. exact fixed-order re-scoring of the survivors: one lane walks one row in k-ascending order with a
+    // single accumulator (the oracle's rounding sequence).  A lane streams its own row as 16-byte loads, 64 bytes
+    // (two sectors) per step with the next step already in flight; the second half of every sector is an L1 hit.
+    if ((a.d & 3) == 0) {
+      const int d4 = a.d >> 2;
+      const float4* qs4 = reinterpret_cast<const float4*>(sm.qs);
+      for (int li = tid; li < nsurv; li += C::kThreads) {
+        const int ei = (int)sm.surv[li];
+        const float4* rp = reinterpret_cast<const float4*>(a.db_f32 + (size_t)sm.ent_row[ei] * a.d);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cur[4], nxt[4];
 #pragma unroll
-        for (int t = 0; t < NL; ++t)
-          rowp[t] = a.db_f32 + (size_t)__shfl_sync(0xffffffffu, my_row, t * RPI + rsub) * a.d;
-        auto load_tile = [&](int k0, float4 (&v)[NL]) {
-          const int col = k0 + c4 * 4;
-#pragma unroll
-          for (int t = 0; t < NL; ++t) {
-            const float* src = rowp[t] + col;
-            if (vec_ok && col + 3 < a.d) {
-              v[t] = *reinterpret_cast<const float4*>(src);
-            } else {
-              v[t].x = col + 0 < a.d ? src[0] : 0.0f;
-              v[t].y = col + 1 < a.d ? src[1] : 0.0f;
-              v[t].z = col + 2 < a.d ? src[2] : 0.0f;
-              v[t].w = col + 3 < a.d ? src[3] : 0.0f;
-            }
-          }
-        };
-        float4 cur[NL], nxt[NL];
-        load_tile(0, cur);
+        for (int t = 0; t < 4; ++t) cur[t] = t < d4 ? __ldg(rp + t) : z;
         float acc = 0.0f;
-        for (int k0 = 0; k0 < a.d; k0 += C::kKc) {
-          const bool more = k0 + C::kKc < a.d;
-          if (more) load_tile(k0 + C::kKc, nxt);
+        for (int k4 = 0; k4 < d4; k4 += 4) {
 #pragma unroll
-          for (int t = 0; t < NL; ++t) {
-            float* dst = tile + (t * RPI + rsub) * (C::kKc + 1) + c4 * 4;
-            dst[0] = cur[t].x; dst[1] = cur[t].y; dst[2] = cur[t].z; dst[3] = cur[t].w;
-          }
-          __syncwarp();
-          const float* mine = tile + lane * (C::kKc + 1);
-          if (a.metric == 0) {
+          for (int t = 0; t < 4; ++t) nxt[t] = k4 + 4 + t < d4 ? __ldg(rp + k4 + 4 + t) : z;
 #pragma unroll
-            for (int kk = 0; kk < C::kKc; ++kk) acc = __fmaf_rn(sm.qs[k0 + kk], mine[kk], acc);
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < C::kKc; ++kk) {
-              const float t = __fsub_rn(sm.qs[k0 + kk], mine[kk]);  // padded columns: 0 - 0
-              acc = __fmaf_rn(t, t, acc);
+          for (int t = 0; t < 4; ++t) {
+            const float4 qv = qs4[k4 + t];  // padded with zeros up to d_round
+            if (a.metric == 0) {
+              acc = __fmaf_rn(qv.x, cur[t].x, acc);
+              acc = __fmaf_rn(qv.y, cur[t].y, acc);
+              acc = __fmaf_rn(qv.z, cur[t].z, acc);
+              acc = __fmaf_rn(qv.w, cur[t].w, acc);
+            } else {  // padded columns: (0 - 0)^2
+              float u = __fsub_rn(qv.x, cur[t].x); acc = __fmaf_rn(u, u, acc);
+              u = __fsub_rn(qv.y, cur[t].y); acc = __fmaf_rn(u, u, acc);
+              u = __fsub_rn(qv.z, cur[t].z); acc = __fmaf_rn(u, u, acc);
+              u = __fsub_rn(qv.w, cur[t].w); acc = __fmaf_rn(u, u, acc);
             }
           }
-          __syncwarp();
-          if (more) {
 #pragma unroll
-            for (int t = 0; t < NL; ++t) cur[t] = nxt[t];
+          for (int t = 0; t < 4; ++t) cur[t] = nxt[t];
+        }
+        atomicMax(&sm.best[sm.ent_slot[ei]], score_key(a.metric == 0 ? acc : -acc));
+      }
+    } else {  // rows are not 16-byte aligned: scalar walk
+      for (int li = tid; li < nsurv; li += C::kThreads) {
+        const int ei = (int)sm.surv[li];
+        const float* rp = a.db_f32 + (size_t)sm.ent_row[ei] * a.d;
+        float acc = 0.0f;
+        for (int j = 0; j < a.d; ++j) {
+          if (a.metric == 0) {
+            acc = __fmaf_rn(sm.qs[j], __ldg(rp + j), acc);
+          } else {
+            const float u = __fsub_rn(sm.qs[j], __ldg(rp + j));
+            acc = __fmaf_rn(u, u, acc);
           }
         }
-        if (live) atomicMax(&sm.best[sm.ent_slot[ei]], score_key(a.metric == 0 ? acc : -acc));
+        atomicMax(&sm.best[sm.ent_slot[ei]], score_key(a.metric == 0 ? acc : -acc));
       }
     }
   }

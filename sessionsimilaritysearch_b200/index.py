@@ -115,7 +115,8 @@ class _FlatIndex:
                 "scan_ns": int(st(self._h, 3)), "scan_launches": int(st(self._h, 4)),
                 "refine_candidates": int(st(self._h, 5)), "refine_rescored": int(st(self._h, 6)),
                 "refine_sessions": int(st(self._h, 7)), "refine_calls": int(st(self._h, 8)),
-                "refine_phase_cycles": [int(st(self._h, 9 + p)) for p in range(7)]}
+                "refine_phase_cycles": [int(st(self._h, 9 + p)) for p in range(7)],
+                "overflow_reason": int(st(self._h, 24))}
 
 
 class IndexFlatIP(_FlatIndex):
