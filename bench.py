@@ -322,6 +322,8 @@ def main():
     waves = inner.stats()["waves"]
     reruns = inner.stats()["reruns"]
     overflow_reason = inner.stats()["overflow_reason"]
+    scan_kernel_name = {"ss": "scan_bf16_kernel", "ts": "scan_bf16_ts_kernel", "2cta": "scan_bf16_2cta_kernel",
+                        "kloop": "scan_bf16_kloop_kernel", "fp32": "scan_fp32_kernel"}[inner.stats()["scan_variant"]]
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
@@ -386,7 +388,7 @@ def main():
         achieved = bytes_per_step / scan_s / 1e9 if scan_s > 0 else 0.0
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
-                    "kernel": "scan_bf16_2cta_kernel", "launches_per_step": scan_ns[1] / a.steps,
+                    "kernel": scan_kernel_name, "launches_per_step": scan_ns[1] / a.steps,
                     "kernel_ms_per_step": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / ms_step,
                     "algorithmic": "rows*d_pad*2 + nq_pad*d_pad*2 B = %.3e per step (nq %d < ridge %.0f)"
                                    % (bytes_per_step, a.nq, ridge),
@@ -396,8 +398,7 @@ def main():
         achieved = flops_per_step / scan_s / 1e12 if scan_s > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind + " sustained bf16",
-                    "kernel": {"ts": "scan_bf16_ts_kernel", "ss": "scan_bf16_kernel"}.get(
-                        os.environ.get("SSS_SCAN_VARIANT", ""), "scan_bf16_2cta_kernel"), "launches_per_step": scan_ns[1] / a.steps,
+                    "kernel": scan_kernel_name, "launches_per_step": scan_ns[1] / a.steps,
                     "kernel_ms_per_step": scan_s * 1e3, "kernel_share_of_step": scan_s * 1e3 / ms_step,
                     "algorithmic": "2*nq*rows*d flop = %.3e per step" % flops_per_step}
     else:

@@ -95,7 +95,8 @@ int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mod
  * sss_index_set_profiling(ix, 1): CUDA events are then recorded around every scan launch on the caller's
  * stream), 5..23 = refine volumes / phase cycles / scan role counters of profiling builds, 24 = bit mask of
  * what overflowed when the last search had to be redone with the safe schedule (1 record sub-region,
- * 2 records per query, 4 candidate list, 8 new candidates, 16 session table, 32 re-score list). */
+ * 2 records per query, 4 candidate list, 8 new candidates, 16 session table, 32 re-score list),
+ * 25 = scan kernel of the last search (0 fp32 CUDA cores, 1 SS, 2 TS, 3 pair, 4 K-loop pair). */
 int64_t sss_index_stat(const sss_index_t* ix, int what);
 int sss_index_set_profiling(sss_index_t* ix, int on);
 

@@ -117,7 +117,7 @@ struct Workspace {
 };
 
 // A growable row store: fixed-order-normalised fp32 rows (rescoring / fp32 scan) and, when the tensor
-// path applies (d <= 128), a zero-padded bf16 copy laid out for TMA (row pitch d_pad*2 bytes).
+// path applies (inner product, d <= 4096), a zero-padded bf16 copy laid out for TMA (row pitch d_pad*2 bytes).
 struct RowStore {
   float* f32 = nullptr;
   void* bf16 = nullptr;
@@ -172,7 +172,7 @@ struct sss_index {
   int64_t* seg_off = nullptr;  // device
   int32_t* row_seg = nullptr;  // device
   Workspace ws;
-  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0, stat_overflow_reason = 0;
+  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0, stat_overflow_reason = 0, stat_variant = 0;
   // optional scan-kernel timing (CUDA events on the launching stream around every scan launch)
   bool profile = false;
   std::vector<cudaEvent_t> ev;
@@ -208,7 +208,7 @@ extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric
   ix->metric = metric;
   ix->id_offset = id_offset;
   ix->num_sms = prop.multiProcessorCount;
-  ix->tensor_ok = ix->d_pad <= 128 && metric == SSS_METRIC_IP;
+  ix->tensor_ok = ix->d_pad <= 4096 && metric == SSS_METRIC_IP;
   *out = ix;
   return 0;
 }
@@ -240,7 +240,8 @@ extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
     case 0: return ix->stat_kernels;
     case 1: return ix->stat_waves;
     case 2: return ix->stat_reruns;
-    case 24: return ix->stat_overflow_reason;  // bit mask of what overflowed in the last rerun (select.cu)
+    case 24: return ix->stat_overflow_reason;
+    case 25: return ix->stat_variant;  // scan of the last search: 0 fp32, 1 SS, 2 TS, 3 pair (2-CTA), 4 K-loop pair  // bit mask of what overflowed in the last rerun (select.cu)
     case 3: return (int64_t)(ix->scan_us * 1000.0);  // scan-kernel time of the last search, ns (profiling on)
     case 4: return ix->scan_launches;
     case 5: return (int64_t)ix->dbg_host[0];  // candidates entering refine (profiling on)
@@ -352,11 +353,11 @@ static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe
     const char* g = getenv("SSS_WAVE_GROWTH");  // tuning: growth factor x10
     const char* f = getenv("SSS_WAVE_FIRST");   // tuning: rows of the first wave
     const int64_t growth10 = g ? std::max<int64_t>(11, atoll(g)) : (few_queries ? 30 : 20);
-    int64_t e = f ? std::max<int64_t>(256, atoll(f) / 256 * 256) : bootstrap_rows;
+    int64_t e = f ? std::max<int64_t>(512, atoll(f) / 512 * 512) : bootstrap_rows;
     e = std::min(e, n_rows);
     ends.push_back(e);
     while (e < n_rows) {
-      int64_t nx = (e * growth10 / 10 + 255) / 256 * 256;
+      int64_t nx = (e * growth10 / 10 + 511) / 512 * 512;
       // do not leave a short tail wave: fold anything below a quarter wave into this one
       if (n_rows - nx < (nx - e) / 4) nx = n_rows;
       e = std::min(n_rows, nx);
@@ -397,10 +398,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   int mode = b.mode;
   if (mode != SSS_MODE_FP32 && !ix->tensor_ok) {
     SSS_REQUIRE(mode == SSS_MODE_EXACT,
-                "SSS_MODE_BF16 needs d <= 128 and the inner-product metric (use SSS_MODE_EXACT or SSS_MODE_FP32)");
+                "SSS_MODE_BF16 needs d <= 4096 and the inner-product metric (use SSS_MODE_EXACT or SSS_MODE_FP32)");
     mode = SSS_MODE_FP32;  // EXACT is defined as "bit-identical to FP32": run the fp32 scan itself
   }
   const bool tensor = mode != SSS_MODE_FP32 && n_rows > 0;
+  ix->stat_variant = 0;
   const int cap = 4096;
   SSS_REQUIRE(b.k <= cap / 2, "k too large (max 2048)");
   const int64_t nq_pad = (b.nq + 127) / 128 * 128;
@@ -422,6 +424,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     // leave shared memory for the refine blocks that co-run with the scan when overlapping
     if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan)) return 1;
     if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
+    ix->stat_variant = plan.kloop ? 4 : plan.two_cta ? 3 : plan.ts ? 2 : 1;
     if (overlap && !ix->side) {
       SSS_CUDA_OK(cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking));
       for (int i = 0; i < 2; ++i) {
@@ -463,7 +466,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     const bool grouped = ix->reduce == SSS_REDUCE_MAX;
     const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
     const char* no_boot = getenv("SSS_NO_BOOTSTRAP");
-    const bool bootstrap = tensor && (plan.ts || plan.two_cta) && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
+    const bool bootstrap = tensor && (plan.ts || plan.two_cta || plan.kloop) && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
                            (int64_t)(b.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4;
     if (bootstrap) {
       const size_t need = (size_t)n_boot_chunks * (size_t)nq_pad;
@@ -505,6 +508,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.rec = wave_tensor ? rec_buf : nullptr;
       ra.rec_cnt = cnt_buf;
       ra.rec_nsub = tensor ? plan.rec_nsub : 0;
+      ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
       ra.row_limit = n_rows;
       // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
       // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever
@@ -780,7 +784,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     RefineArgs ra;
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
-    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.row_limit = ix->n; ra.debug = nullptr;
+    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.row_limit = ix->n; ra.debug = nullptr;
     std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
     int64_t begin = 0;
     for (int64_t end : ends) {

@@ -35,7 +35,9 @@ struct Bf16ScanPlan {
   bool ts;          // query tiles resident in TMEM (A operand from TMEM) instead of shared memory
   bool two_cta;     // cta_group::2 pairs: M=256 x N=256 MMAs, each CTA loads half of every DB tile
   int rec_nsub;     // record sub-regions per query
-  int tile_rows;    // DB rows per tile (128, or 256 for the 2-CTA variant)
+  int tile_rows;    // DB rows per tile (128, 256 for the 2-CTA variant, 512 for the K-loop variant)
+  bool kloop;       // wide rows (d_pad > 128): both operands streamed per K block, one query group per CTA pair
+  int groups;       // K-loop variant: query groups of 256
 };
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
@@ -64,6 +66,7 @@ struct RefineArgs {
   const HitRecord* rec;      // tensor-core hit records of this wave, or nullptr for list input
   const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
   int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
+  int rec_cap;               // records per sub-region (16; 64 for the K-loop scan)
   int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill
   unsigned long long* debug; // optional [12]: sums of candidates, re-scored rows, sessions, refines, then cycles per refine phase
 };

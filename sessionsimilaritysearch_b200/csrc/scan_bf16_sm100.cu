@@ -178,6 +178,7 @@ struct ScanParams {
   int dbg;               // experiments only (SSS_SCAN_DBG): 1 = read half of the accumulator columns, 2 = read all, test half
   float* cmax;           // bootstrap mode: write the max of every 32-row chunk to cmax[chunk * nq_pad + q] instead
                          // of filtering (chunk counted from row_begin)
+  int groups;            // K-loop variant: query groups of 256 (one per CTA pair)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -887,6 +888,208 @@ scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
 }
 
+// ======================================================================================================
+// scan_bf16_kloop_kernel — any width (d_pad a multiple of 64, up to 4096): BOTH operands are streamed per
+// 64-wide K block, the accumulators stay in TMEM for the whole K sweep.  This is the tensor path of the
+// encoder-shaped embeddings (d = 1600, model/gnn.py:184-191), whose query tiles do not fit in shared memory.
+//
+// Cluster (2,1,1), cta_group::2.  Pair p serves ONE query group g = p % G (256 queries: 128 per CTA) and the DB
+// super-tiles T = p / G + n * (pairs / G); a super-tile is 512 rows = two 256-row MMA tiles, one per 256-column
+// TMEM slot, so that one query K block feeds eight MMAs:
+//   stage = [A: 128 queries x 64 | B0: my 128 rows of tile 2T x 64 | B1: my 128 rows of tile 2T+1 x 64] = 48 KB per CTA
+//   per stage 2 x 4 MMAs of M=256 x N=256 x K=16 = 1024 tensor cycles per 48 KB per SM (47 B/clk, under the
+//   ~42-64 B/clk/SM an SM can pull from L2; a single 256-row tile per sweep would need 64 B/clk).
+// Pairs p .. p+G-1 walk the same super-tile at the same time with different query groups, so a DB tile comes from
+// HBM once and from L2 for the other groups; the query matrix (nq_pad x d_pad bf16, a few MB) lives in L2.
+// Both slots are drained after the sweep (warpgroup w takes slot w) — no TMEM double buffering: the exposed
+// epilogue is ~2000 cycles against num_kb * 1024 cycles of MMA (7 % at d = 1600).
+constexpr int kKloopStageBytes = 3 * kKBlockBytes;
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+scan_bf16_kloop_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                       const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = (int)(blockIdx.x >> 1);
+  const int n_pairs = (int)(gridDim.x >> 1);
+  const int G = p.groups;
+  const int g = pair % G;            // query group of this pair
+  const int pig = pair / G;          // pair index inside the group
+  const int ppg = n_pairs / G;       // pairs per group (the grid is G * ppg pairs)
+  const int nq_pad = p.total_mtiles * kTileQ;
+  const int n_super = (int)p.n_tiles;  // 512-row super-tiles in this wave
+  const int my_items = pig < n_super ? (n_super - 1 - pig) / ppg + 1 : 0;
+  const int mt = 2 * g + (int)rank;    // m-tile of this CTA (may be one past the end for an odd tile count)
+
+  const uint32_t bar_base = smem_base + (uint32_t)(p.num_stages * kKloopStageBytes);
+  const uint32_t full_bar = bar_base;                         // [kMaxStages] (leader's are used)
+  const uint32_t empty_bar = bar_base + 8 * kMaxStages;       // [kMaxStages]
+  const uint32_t tfull_bar = bar_base + 16 * kMaxStages;      // [1]
+  const uint32_t tempty_bar = tfull_bar + 8;                  // [1] (leader's is used)
+  const uint32_t tmem_ptr_addr = tempty_bar + 8;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_db);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 16);  // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own half of A, B0, B1 for every K block =====================
+    if (lane == 0 && my_items > 0) {
+      const uint32_t leader_full = map_to_cta(full_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int T = pig + it * ppg;
+        const int row0 = (int)p.row_begin + T * 512 + (int)rank * kTileRows;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 401);
+          if (leader) mbar_expect_tx(full_bar + 8 * stage, 2u * (uint32_t)kKloopStageBytes);
+          const uint32_t dst = smem_base + (uint32_t)(stage * kKloopStageBytes);
+          tma_load_2d_2sm(dst, &tmap_q, leader_full + 8 * stage, kb * 64, mt * kTileQ);
+          tma_load_2d_2sm(dst + kKBlockBytes, &tmap_db, leader_full + 8 * stage, kb * 64, row0);
+          tma_load_2d_2sm(dst + 2 * kKBlockBytes, &tmap_db, leader_full + 8 * stage, kb * 64, row0 + 256);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && my_items > 0) {  // whole warp, uniform: one elected lane issues
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_items; ++it) {
+        mbar_wait(tempty_bar, ((uint32_t)it & 1u) ^ 1u, p.err_flag, 404);  // both slots drained (item it - 1)
+        tc_fence_after();
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 403);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + (uint32_t)(stage * kKloopStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sbase);
+          const uint64_t b0desc = umma_desc_sw128(sbase + kKBlockBytes);
+          const uint64_t b1desc = umma_desc_sw128(sbase + 2 * kKBlockBytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t acc = (kb | k4) != 0 ? 1u : 0u;
+            umma_bf16_2cta(tmem_base, adesc + (uint64_t)(2 * k4), b0desc + (uint64_t)(2 * k4), acc);
+            umma_bf16_2cta(tmem_base + 256u, adesc + (uint64_t)(2 * k4), b1desc + (uint64_t)(2 * k4), acc);
+          }
+          umma_commit_2cta(empty_bar + 8 * stage);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2cta(tfull_bar);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): warpgroup w drains slot w (256 columns) ==========
+    const int wg = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t leader_tempty = map_to_cta(tempty_bar, 0);
+    const uint32_t qidx = (uint32_t)(mt * kTileQ + quarter * 32 + lane);
+    const bool q_ok = qidx < (uint32_t)nq_pad;
+    const uint32_t sub_stride = (uint32_t)ppg * 2u;
+    const uint32_t my_sub = (uint32_t)pig * 2u + (uint32_t)wg;
+    HitRecord* myrec = p.rec + ((size_t)(q_ok ? qidx : 0u) * sub_stride + my_sub) * (size_t)p.rec_cap;
+    uint32_t rc = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int T = pig + it * ppg;
+      const uint32_t row_tile = (uint32_t)((int)p.row_begin + T * 512 + wg * 256);
+      const float thr = q_ok ? p.st.thr[qidx] : INFINITY;
+      mbar_wait(tfull_bar, (uint32_t)it & 1u, p.err_flag, 405);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + (uint32_t)wg * 256u;
+      auto process = [&](const uint32_t (&r)[32], int c) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+        float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]);
+        float m2 = max3(f[6], f[7], f[8]), m3 = max3(f[9], f[10], f[11]);
+        m0 = max3(m0, f[12], f[13]); m1 = max3(m1, f[14], f[15]);
+        m2 = max3(m2, f[16], f[17]); m3 = max3(m3, f[18], f[19]);
+        m0 = max3(m0, f[20], f[21]); m1 = max3(m1, f[22], f[23]);
+        m2 = max3(m2, f[24], f[25]); m3 = max3(m3, f[26], f[27]);
+        m0 = max3(m0, f[28], f[29]); m1 = max3(m1, f[30], f[31]);
+        const float mx = fmaxf(max3(m0, m1, m2), m3);
+        if (p.cmax != nullptr) {
+          if (q_ok) {
+            const uint32_t chunk = (row_tile - (uint32_t)p.row_begin) / 32u + (uint32_t)c;
+            p.cmax[(size_t)chunk * (size_t)nq_pad + qidx] = mx;
+          }
+          return;
+        }
+        const bool hit = mx > thr;
+        if (__any_sync(0xffffffffu, hit)) {
+          if (hit) {
+            if (rc < (uint32_t)p.rec_cap) {
+              uint4* dst = reinterpret_cast<uint4*>(myrec + rc);
+              dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[1 + i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+            ++rc;
+          }
+        }
+      };
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld32(taddr + (uint32_t)((c + 1) * 32), rb);
+        process(ra, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) {
+          tmem_ld32(taddr + (uint32_t)((c + 2) * 32), ra);
+        } else {  // all eight chunks have left TMEM: hand the slot back to the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar);
+            else mbar_arrive_remote(leader_tempty);
+          }
+        }
+        process(rb, c + 1);
+        if (c + 2 < 8) tmem_ld_wait();
+      }
+    }
+    if (q_ok) p.rec_cnt[(size_t)qidx * sub_stride + my_sub] = rc;
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -921,9 +1124,38 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
 }
 
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan) {
-  SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 128, "tensor-core scan supports d <= 128");
+  SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 4096, "tensor-core scan supports d <= 4096");
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
+  plan->kloop = false;
+  plan->groups = 0;
+  if (d_pad > 128) {
+    // wide rows: the K-loop pair kernel (both operands streamed per K block)
+    const int G = (total_mtiles + 1) / 2;
+    const int n_pairs = num_sms / 2;
+    SSS_REQUIRE(G <= n_pairs, "query batch too large for the K-loop scan (split it)");
+    const int ppg = n_pairs / G;
+    plan->kloop = true;
+    plan->ts = false;
+    plan->two_cta = false;
+    plan->groups = G;
+    plan->num_kb = d_pad / 64;
+    plan->num_mt = 1;
+    plan->total_mtiles = total_mtiles;
+    plan->grid_x = 2 * G * ppg;
+    plan->grid_y = 1;
+    int stages = (227 * 1024 - 1024 - kBarrierBytes) / kKloopStageBytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > max_stages) stages = max_stages;
+    SSS_REQUIRE(stages >= 2, "not enough shared memory for the operand ring");
+    plan->num_stages = stages;
+    plan->smem_bytes = 1024 + stages * kKloopStageBytes + kBarrierBytes;
+    plan->rec_cap = 4 * kRecSubCap;  // a query has ppg * 2 sub-regions here, a quarter of the d <= 128 kernels'
+    plan->rec_nsub = ppg * 2;
+    plan->n_regions = (int)nq_pad * plan->rec_nsub;
+    plan->tile_rows = 512;
+    return 0;
+  }
   plan->num_kb = d_pad / 64;
   plan->total_mtiles = total_mtiles;
   plan->grid_y = (total_mtiles + 3) / 4;
@@ -985,7 +1217,8 @@ unsigned long long* scan_prof_buffer() { return g_scan_prof; }
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream) {
-  SSS_REQUIRE(cmax == nullptr || plan.ts || plan.two_cta, "chunk-max bootstrap needs the TS or 2-CTA scan variant");
+  SSS_REQUIRE(cmax == nullptr || plan.ts || plan.two_cta || plan.kloop,
+              "chunk-max bootstrap needs the TS, 2-CTA or K-loop scan variant");
   SSS_REQUIRE(row_begin % plan.tile_rows == 0, "scan wave must start on a tile boundary");
   ScanParams p;
   p.num_kb = plan.num_kb;
@@ -1001,6 +1234,7 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.err_flag = err_flag;
   p.q_bf16 = (const uint4*)q_bf16;
   p.cmax = cmax;
+  p.groups = plan.groups;
   {
     const char* dbg = getenv("SSS_SCAN_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
@@ -1021,10 +1255,12 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
                                      plan.smem_bytes));
     SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      plan.smem_bytes));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kloop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     plan.smem_bytes));
     smem_set = plan.smem_bytes;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  if (plan.two_cta) {
+  if (plan.two_cta || plan.kloop) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kNumThreads);
@@ -1037,8 +1273,12 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel, *(const CUtensorMap*)tmap_q,
-                                   *(const CUtensorMap*)tmap_db, p));
+    if (plan.kloop)
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_kloop_kernel, *(const CUtensorMap*)tmap_q,
+                                     *(const CUtensorMap*)tmap_db, p));
+    else
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel, *(const CUtensorMap*)tmap_q,
+                                     *(const CUtensorMap*)tmap_db, p));
   } else if (plan.ts)
     scan_bf16_ts_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_db, p);
   else

@@ -205,9 +205,9 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         uint32_t cnt = 0;
         if (s0 + lane < nsub) {
           cnt = a.rec_cnt[sub0 + s0 + lane];
-          if (cnt > (uint32_t)kRecSubCap) {
+          if (cnt > (uint32_t)a.rec_cap) {
             atomicOr(st.overflow, 1);   // reason codes: sss_index_stat(ix, 24)
-            cnt = kRecSubCap;
+            cnt = (uint32_t)a.rec_cap;
           }
         }
         uint32_t inc = cnt;
@@ -231,7 +231,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     for (int s = tid; s < nsub; s += C::kThreads) {
       const uint32_t b0 = sm.subpre[s], b1 = sm.subpre[s + 1];
       for (uint32_t j = b0; j < b1 && j < (uint32_t)C::kRmax; ++j)
-        sm.recptr[j] = (uint32_t)((sub0 + s) * kRecSubCap + (j - b0));
+        sm.recptr[j] = (uint32_t)((sub0 + s) * (size_t)a.rec_cap + (j - b0));
     }
     __syncthreads();
     // a warp takes eight records per round: eight independent 128-byte loads in flight, lane = score index

@@ -116,7 +116,8 @@ class _FlatIndex:
                 "refine_candidates": int(st(self._h, 5)), "refine_rescored": int(st(self._h, 6)),
                 "refine_sessions": int(st(self._h, 7)), "refine_calls": int(st(self._h, 8)),
                 "refine_phase_cycles": [int(st(self._h, 9 + p)) for p in range(7)],
-                "overflow_reason": int(st(self._h, 24))}
+                "overflow_reason": int(st(self._h, 24)),
+                "scan_variant": ("fp32", "ss", "ts", "2cta", "kloop")[int(st(self._h, 25))]}
 
 
 class IndexFlatIP(_FlatIndex):

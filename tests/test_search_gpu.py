@@ -205,6 +205,32 @@ def test_million_rows_exact_equals_fp32_and_oracle_sample(sss, oracle):
     assert recall >= 0.98 and np.max(np.abs(Db - D)) <= 2e-3, recall  # raw bf16: tail of 1e5 scores reaches ~1.1e-3
 
 
+@pytest.mark.parametrize("d,n,nq", [(256, 300000, 300), (1600, 270000, 130)])
+def test_wide_rows_take_the_kloop_tensor_path(sss, oracle, d, n, nq):
+    """d > 128 (the encoder's 1600-wide embeddings): K-loop pair kernel, bootstrapped thresholds, session max.
+    exact mode must equal the bit-faithful fp32 mode (itself pinned to the oracle above) in ids and scores."""
+    seg = make_segments(n, 30)
+    db = make_session_rows(seg, d, 31)
+    q = make_iid(nq, d, 32)
+    ix = sss.build_index(db, 'cos', mode="exact")
+    ix.set_segments(seg, "max")
+    qn = sss.normalize(q)
+    D, I = ix.search(qn, 50)
+    st = ix.stats()
+    assert st["scan_variant"] == "kloop" and st["reruns"] == 0, st
+    D2, I2 = ix.search(qn, 50, mode="fp32")
+    assert ix.stats()["scan_variant"] == "fp32"
+    _assert_exact(D, I, D2, I2)
+    sub = np.arange(0, nq, max(1, nq // 4))[:4]
+    Do, Io = oracle.search_flat(oracle.normalize(db[:20000], oracle.NORM_UTIL), oracle.normalize(q[sub], oracle.NORM_UTIL), 10)
+    ix2 = sss.build_index(db[:20000], 'cos', mode="exact")
+    Ds, Is = ix2.search(qn[sub], 10)
+    _assert_exact(Ds, Is, Do, Io)
+    Db, Ib = ix.search(qn, 50, mode="bf16")
+    recall = np.mean([len(set(Ib[r]) & set(I[r])) / 50.0 for r in range(nq)])
+    assert recall >= 0.97 and np.max(np.abs(Db - D)) <= 3e-3, recall
+
+
 def test_torch_device_tensors(sss, oracle):
     import torch
     db = make_iid(10000, 128, 21)
