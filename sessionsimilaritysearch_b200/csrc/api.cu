@@ -484,6 +484,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, grouped, bootstrap ? kBootRows : 0, tensor && plan.total_mtiles == 1);
     int64_t begin = 0;
     uint32_t wave_id = 0;
+    const char* nl_env = getenv("SSS_NO_LAZY");  // A/B switch: exact re-scoring in every wave
+    const bool no_lazy = nl_env && nl_env[0] == '1';
     bool prev_tensor = false;
     for (int64_t end : ends) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -509,6 +511,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.rec_cnt = cnt_buf;
       ra.rec_nsub = tensor ? plan.rec_nsub : 0;
       ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
+      ra.lazy = (mode == SSS_MODE_EXACT && attempt == 0 && b.k <= 256 && !no_lazy) ? 1 : 0;
+      ra.final = end == ends.back() ? 1 : 0;
       ra.row_limit = n_rows;
       // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
       // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever
@@ -784,7 +788,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     RefineArgs ra;
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
-    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.row_limit = ix->n; ra.debug = nullptr;
+    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.lazy = 0; ra.final = 1; ra.row_limit = ix->n; ra.debug = nullptr;
     std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
     int64_t begin = 0;
     for (int64_t end : ends) {

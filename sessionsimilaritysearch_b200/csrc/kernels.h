@@ -67,6 +67,8 @@ struct RefineArgs {
   const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
   int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
   int rec_cap;               // records per sub-region (16; 64 for the K-loop scan)
+  int lazy;                  // EXACT mode: keep candidate rows with tensor-core keys, re-score in the last wave
+  int final;                 // last wave of the search
   int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill
   unsigned long long* debug; // optional [12]: sums of candidates, re-scored rows, sessions, refines, then cycles per refine phase
 };

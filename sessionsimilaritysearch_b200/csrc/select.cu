@@ -180,7 +180,18 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int NW = C::kThreads / 32;
-  const int nr = (int)st.nret[q];
+  // Lazy representation (EXACT mode, tensor-core waves only): the retained entries [0, nl) are candidate ROWS with
+  // their tensor-core keys (bit 31 of nret marks it) and the exact re-scoring is deferred to the last wave.  With m
+  // the filter slack (|exact - tensor| <= m) and b_k the k-th best session by tensor-core score: k sessions have an
+  // exact score >= b_k - m, so a session whose best tensor-core score is below b_k - 2m, and inside a live session a
+  // row more than 2m below the session's best, can never decide the result.  What survives that test is kept as
+  // rows; the last wave (or a query whose band outgrows the list) re-scores the survivors once and continues in
+  // the eager representation (one exact entry per session).
+  const uint32_t nret_raw = st.nret[q];
+  const int nr_all = (int)(nret_raw & 0x7FFFFFFFu);
+  const bool lazy = a.lazy != 0 && a.rescore != 0 && a.rec != nullptr && ((nret_raw >> 31) != 0u || nr_all == 0);
+  const int nr = lazy ? 0 : nr_all;   // retained exact entries
+  const int nl = lazy ? nr_all : 0;   // retained lazy rows
   uint64_t* g = st.cand + (size_t)q * st.cap;
   const float margin = st.margin[q];
   const float thr = st.thr[q];
@@ -191,26 +202,34 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     sm.owner[h] = 0u;
     sm.best[h] = 0u;
   }
-  if (tid < 4) sm.ctr[tid] = 0;
+  if (tid < 4) sm.ctr[tid] = tid == 0 ? nl : 0;
   if (tid == 0) sm.subpre[0] = 0u;
+  if (nl > C::kKmax && !C::kLast) return RF_SKIP;
+  for (int i = tid; i < nl; i += C::kThreads) {  // lazy rows re-enter as candidates in front of the new ones
+    const uint64_t e = g[i];
+    sm.ent_key[i] = cand_key(e);
+    sm.ent_row[i] = cand_id(e);
+  }
   __syncthreads();
 
   // ---- A. compact the new candidates into shared memory
   if (a.rec != nullptr) {
     const int nsub = a.rec_nsub;
     const size_t sub0 = (size_t)q * nsub;
-    if (warp == 0) {  // record counts of the query's sub-regions -> exclusive prefix
+    // record counts of the query's sub-regions: one load per thread, then an exclusive prefix by warp 0
+    for (int s = tid; s < nsub; s += C::kThreads) {
+      uint32_t cnt = a.rec_cnt[sub0 + s];
+      if (cnt > (uint32_t)a.rec_cap) {
+        atomicOr(st.overflow, 1);   // reason codes: sss_index_stat(ix, 24)
+        cnt = (uint32_t)a.rec_cap;
+      }
+      sm.subpre[s + 1] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
       uint32_t run = 0;
       for (int s0 = 0; s0 < nsub; s0 += 32) {
-        uint32_t cnt = 0;
-        if (s0 + lane < nsub) {
-          cnt = a.rec_cnt[sub0 + s0 + lane];
-          if (cnt > (uint32_t)a.rec_cap) {
-            atomicOr(st.overflow, 1);   // reason codes: sss_index_stat(ix, 24)
-            cnt = (uint32_t)a.rec_cap;
-          }
-        }
-        uint32_t inc = cnt;
+        uint32_t inc = s0 + lane < nsub ? sm.subpre[s0 + lane + 1] : 0u;
         for (int o = 1; o < 32; o <<= 1) {
           uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += t;
@@ -222,7 +241,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     __syncthreads();
     RF_PHASE(0);  // init + sub-region counts
     const int R = (int)sm.subpre[nsub];
-    if (R == 0) return RF_DONE;  // nothing new since the last refine
+    if (R == 0 && !(lazy && a.final != 0 && nl > 0)) return RF_DONE;  // nothing new since the last refine
     if (R > C::kRmax) {
       if (!C::kLast) return RF_SKIP;
       if (tid == 0) atomicOr(st.overflow, 2);
@@ -234,25 +253,47 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         sm.recptr[j] = (uint32_t)((sub0 + s) * (size_t)a.rec_cap + (j - b0));
     }
     __syncthreads();
-    // a warp takes eight records per round: eight independent 128-byte loads in flight, lane = score index
-    constexpr int RU = 8;
-    for (int r0 = warp * RU; r0 < Rc; r0 += NW * RU) {
-      float v[RU];
-      uint32_t row[RU];
+    // one thread per record: its nine 16-byte loads are independent, so a block sees ONE global latency for all
+    // of the query's records; the few scores that pass are re-read (L1) when they are appended
+    for (int r0 = 0; r0 < Rc; r0 += C::kThreads) {
+      const int ri = r0 + tid;
+      uint32_t mask = 0u, row_base = 0u;
+      const HitRecord* r = nullptr;
+      if (ri < Rc) {
+        r = a.rec + sm.recptr[ri];
+        const uint4* rv = reinterpret_cast<const uint4*>(r->v);
+        row_base = r->row_base;
+        uint4 x[8];
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const HitRecord* r = a.rec + sm.recptr[r0 + u < Rc ? r0 + u : r0];
-        v[u] = r->v[lane];
-        row[u] = r->row_base + (uint32_t)lane;
-      }
+        for (int i = 0; i < 8; ++i) x[i] = rv[i];
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const bool pass = r0 + u < Rc && v[u] > thr && (int64_t)row[u] < a.row_limit;
-        const int pos = warp_append(&sm.ctr[0], pass);
-        if (pos >= 0 && pos < C::kNc) {
-          sm.ent_key[pos] = score_key(v[u]);
-          sm.ent_row[pos] = row[u];
+        for (int i = 0; i < 8; ++i) {
+          mask |= (__uint_as_float(x[i].x) > thr ? 1u : 0u) << (4 * i);
+          mask |= (__uint_as_float(x[i].y) > thr ? 1u : 0u) << (4 * i + 1);
+          mask |= (__uint_as_float(x[i].z) > thr ? 1u : 0u) << (4 * i + 2);
+          mask |= (__uint_as_float(x[i].w) > thr ? 1u : 0u) << (4 * i + 3);
         }
+        const int64_t room = a.row_limit - (int64_t)row_base;  // rows past the end of the index (last tile)
+        if (room < 32) mask = room <= 0 ? 0u : (mask & ((1u << (int)room) - 1u));
+      }
+      const int mine = __popc(mask);
+      int inc = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int base = 0;
+      if (lane == 31 && inc > 0) base = atomicAdd(&sm.ctr[0], inc);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + inc - mine;
+      while (mask != 0u) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        if (pos < C::kNc) {
+          sm.ent_key[pos] = score_key(r->v[bit]);
+          sm.ent_row[pos] = row_base + (uint32_t)bit;
+        }
+        ++pos;
       }
     }
   } else {
@@ -272,8 +313,6 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     }
     if (tid == 0) sm.ctr[0] = n - nr;
   }
-  if (a.rescore)
-    for (int j = tid; j < d_round; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
   // retained entries own their slots and keep their (final) keys
   for (int i = tid; i < nr; i += C::kThreads) {
     const uint64_t e = g[i];
@@ -319,8 +358,62 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     }
   }
 
+  float t_lo = -INFINITY;  // session-level floor of the survivors (eager: none — it costs more than it saves)
+  float new_thr = thr;
+  if (lazy) {
+    // ---- S. k-th best session by tensor-core score -> floor b_k - 2 * margin (rounded down: conservative).
+    // Three 8-bit radix passes over the session table; the low 8 key bits are left zero, i.e. the result is a lower
+    // bound of b_k within 2^-15 relative — any lower bound keeps the pruning valid.
+    if ((sm.ctr[3] & 0x3FFFFFFF) >= a.k) {
+      int* hist = reinterpret_cast<int*>(sm.tmp);  // [256] bins + [2] result
+      uint32_t prefix = 0u;
+      int rem = a.k;
+      for (int pass = 0; pass < 3; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 256; i += C::kThreads) hist[i] = 0;
+        __syncthreads();
+        for (int h = tid; h < C::kSlots; h += C::kThreads) {
+          const uint32_t key = sm.best[h];
+          if (sm.owner[h] != 0u && (pass == 0 || (key >> (shift + 8)) == prefix))
+            atomicAdd(&hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {  // lane l owns bins 255-8l .. 248-8l (descending)
+          int c[8], s = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            c[j] = hist[255 - 8 * lane - j];
+            s += c[j];
+          }
+          int incl = s;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int run = incl - s;
+          if (run < rem && rem <= incl) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (run < rem && rem <= run + c[j]) {
+                hist[256] = 255 - 8 * lane - j;
+                hist[257] = rem - run;
+              }
+              run += c[j];
+            }
+          }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | (uint32_t)hist[256];
+        rem = hist[257];
+        __syncthreads();
+      }
+      t_lo = __fsub_rd(key_score(prefix << 8), 2.0f * margin);
+      new_thr = fmaxf(thr, t_lo);
+    }
+    RF_PHASE(3);  // lazy: k-th best session
+  }
+
   if (a.rescore) {
-    const float t_lo = -INFINITY;  // (a session-level pre-selection costs more instructions than it saves)
     // ---- C. survivors: rows of live sessions within 2 * margin of their session's best tensor-core score
     for (int i0 = warp * 32; i0 < n_ent; i0 += C::kThreads) {
       const int i = i0 + lane;
@@ -339,6 +432,29 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
       if (tid == 0) atomicOr(st.overflow, 32);
       nsurv = C::kSurv;
     }
+    if (lazy && a.final == 0) {
+      if (nsurv <= C::kKmax) {
+        // ---- W. stay lazy: the surviving rows with their tensor-core keys are the retained set
+        for (int i = tid; i < nsurv; i += C::kThreads) {
+          const int ei = (int)sm.surv[i];
+          g[i] = pack_cand(sm.ent_key[ei], sm.ent_row[ei]);
+        }
+        if (tid == 0) {
+          st.cnt[q] = (uint32_t)nsurv;
+          st.nret[q] = nsurv > 0 ? ((uint32_t)nsurv | 0x80000000u) : 0u;
+          st.thr[q] = new_thr;
+          if (a.debug != nullptr) {
+            atomicAdd(&a.debug[0], (unsigned long long)n_ent);
+            atomicAdd(&a.debug[2], (unsigned long long)(sm.ctr[3] & 0x3FFFFFFF));
+            atomicAdd(&a.debug[3], 1ull);
+          }
+        }
+        RF_PHASE(4);
+        return RF_DONE;
+      }
+      if (!C::kLast) return RF_SKIP;  // the band outgrew the small list: the large instantiation decides
+    }
+    for (int j = tid; j < d_round; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
     // final keys only from here on: retained entries keep theirs, survivors get exact ones
     for (int h = tid; h < C::kSlots; h += C::kThreads) sm.best[h] = 0u;
     __syncthreads();
@@ -431,7 +547,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     st.cnt[q] = m;
     st.nret[q] = m;
     // thresholds only ever rise (a bootstrap threshold may already be in place while fewer than k sessions passed)
-    st.thr[q] = m == a.k ? fmaxf(thr, key_score(cand_key(sm.A[a.k - 1])) - margin) : thr;
+    st.thr[q] = m == a.k ? fmaxf(new_thr, key_score(cand_key(sm.A[a.k - 1])) - margin) : new_thr;
   }
   return RF_DONE;
 }
