@@ -199,6 +199,18 @@ def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
     torch.cuda.synchronize()
     out = {"encoder_sessions_per_s": n_sessions / (e0.elapsed_time(e1) * 1e-3),
            "encoder_nodes_per_batch": int(batches[0]['query'].x.shape[0] + batches[0]['product'].x.shape[0])}
+    try:  # dense linears on the bf16 tensor cores (cuBLAS fp32 emulation), when the loaded cuBLAS has it
+        enc.set_math("bf16x9")
+        for b in batches[:2]:
+            enc(b)
+        e0.record()
+        for b in batches:
+            enc(b)
+        e1.record()
+        torch.cuda.synchronize()
+        out["encoder_bf16x9_sessions_per_s"] = n_sessions / (e0.elapsed_time(e1) * 1e-3)
+    except RuntimeError as e:
+        out["encoder_bf16x9_sessions_per_s"] = "unavailable: %s" % str(e)[:80]
     if not no_cpu:
         from oracle import encoder_oracle as eo
         cb = eo.batch_from_pyg(graph.collate(graphs[:batch]))

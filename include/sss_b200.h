@@ -179,6 +179,14 @@ typedef struct sss_graph_batch {
 int sss_encoder_forward(sss_encoder_t* enc, const sss_graph_batch_t* batch, float* out, int32_t* nonfinite,
                         void* stream);
 
+/* Arithmetic of the encoder's dense linears.  SSS_ENCODER_MATH_FP32 (default): cuBLAS sgemm, pedantic fp32 on the
+ * CUDA cores.  SSS_ENCODER_MATH_BF16X9: cuBLAS' fp32 emulation on the bf16 tensor cores (each operand split into
+ * three bf16 terms, nine products, fp32-level accuracy; cuBLAS >= 12.9 on sm_100) — returns non-zero and leaves the
+ * mode unchanged when the loaded cuBLAS does not offer it.  sss_encoder_get_math returns the active mode. */
+enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1 };
+int sss_encoder_set_math(sss_encoder_t* enc, int math);
+int sss_encoder_get_math(const sss_encoder_t* enc);
+
 /* BinarizeHead eval forward, mlp=None (model/model.py:117-138): out = sign(x W^T + b) in {-1,0,+1}.
  * x [n, in], W [out, in], b [out], out [n, out]; device pointers. */
 int sss_binarize_head(const float* x, const float* W, const float* b, int64_t n, int in_dim, int out_dim,

@@ -56,6 +56,8 @@ SIGNATURES = {
     "sss_encoder_destroy": (c_int, [c_vp]),
     "sss_encoder_set_param": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_int, c_vp]),
     "sss_encoder_forward": (c_int, [c_vp, ctypes.POINTER(GraphBatch), c_vp, c_vp, c_vp]),
+    "sss_encoder_set_math": (c_int, [c_vp, c_int]),
+    "sss_encoder_get_math": (c_int, [c_vp]),
     "sss_binarize_head": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp]),
 }
 

@@ -28,6 +28,7 @@ typedef int (*cublasCreate_t)(cublasHandle_t*);
 typedef int (*cublasDestroy_t)(cublasHandle_t);
 typedef int (*cublasSetStream_t)(cublasHandle_t, cudaStream_t);
 typedef int (*cublasSetMathMode_t)(cublasHandle_t, int);
+typedef int (*cublasSetEmulationStrategy_t)(cublasHandle_t, int);
 typedef int (*cublasSgemm_t)(cublasHandle_t, int, int, int, int, int, const float*, const float*, int, const float*,
                              int, const float*, float*, int);
 struct Cublas {
@@ -37,6 +38,7 @@ struct Cublas {
   cublasSetStream_t set_stream = nullptr;
   cublasSetMathMode_t set_math = nullptr;
   cublasSgemm_t sgemm = nullptr;
+  cublasSetEmulationStrategy_t set_emulation = nullptr;  // cuBLAS >= 12.9 only
   bool load() {
     if (lib) return true;
     const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
@@ -50,11 +52,12 @@ struct Cublas {
     set_stream = (cublasSetStream_t)dlsym(lib, "cublasSetStream_v2");
     set_math = (cublasSetMathMode_t)dlsym(lib, "cublasSetMathMode");
     sgemm = (cublasSgemm_t)dlsym(lib, "cublasSgemm_v2");
+    set_emulation = (cublasSetEmulationStrategy_t)dlsym(lib, "cublasSetEmulationStrategy");
     return create && destroy && set_stream && set_math && sgemm;
   }
 };
 static Cublas g_cublas;
-constexpr int kOpN = 0, kOpT = 1, kPedanticMath = 2;
+constexpr int kOpN = 0, kOpT = 1, kPedanticMath = 2, kBf16x9Math = 4, kEmulationEager = 2;
 
 // row-major C[M,N] (ldc) = A[M,K] (lda) * B^T, B row-major [N,K] (ldb)      (x @ W.T, torch nn.Linear)
 static int gemm_nt(cublasHandle_t h, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
@@ -329,6 +332,7 @@ struct sss_encoder {
   std::map<std::string, float*> params;
   std::map<std::string, int64_t> numel;
   cublasHandle_t blas = nullptr;
+  int math = SSS_ENCODER_MATH_FP32;
   // Workspace arena: slabs are bump-allocated per forward call and kept across calls (cudaMalloc/cudaFree per
   // buffer cost more than the whole forward).  A call that needed more than one slab is followed by one
   // consolidation at the start of the next call; `done` orders reuse across streams.
@@ -448,6 +452,28 @@ extern "C" int sss_encoder_create(sss_encoder_t** out, int device, const sss_enc
   *out = e;
   return 0;
 }
+
+extern "C" int sss_encoder_set_math(sss_encoder_t* e, int math) {
+  SSS_REQUIRE(e != nullptr, "sss_encoder_set_math: NULL encoder");
+  SSS_REQUIRE(math == SSS_ENCODER_MATH_FP32 || math == SSS_ENCODER_MATH_BF16X9, "sss_encoder_set_math: unknown mode");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(e->device);
+  int rc;
+  if (math == SSS_ENCODER_MATH_BF16X9) {
+    rc = g_cublas.set_emulation ? g_cublas.set_math(e->blas, kBf16x9Math) : 1;
+    if (rc == 0) rc = g_cublas.set_emulation(e->blas, kEmulationEager);
+    if (rc != 0) g_cublas.set_math(e->blas, kPedanticMath);
+  } else {
+    rc = g_cublas.set_math(e->blas, kPedanticMath);
+  }
+  cudaSetDevice(prev);
+  SSS_REQUIRE(rc == 0, "the loaded cuBLAS does not offer fp32 emulation on bf16 tensor cores (BF16x9 needs cuBLAS >= 12.9)");
+  e->math = math;
+  return 0;
+}
+
+extern "C" int sss_encoder_get_math(const sss_encoder_t* e) { return e ? e->math : -1; }
 
 extern "C" int sss_encoder_destroy(sss_encoder_t* e) {
   if (!e) return 0;

@@ -59,6 +59,16 @@ class SessionEncoder:
             n += 1
         return n
 
+    def set_math(self, math):
+        """'fp32' (cuBLAS pedantic sgemm, default) or 'bf16x9' (cuBLAS fp32 emulation on the bf16 tensor cores);
+        raises RuntimeError when the loaded cuBLAS does not offer the emulation"""
+        check(self._lib.sss_encoder_set_math(self._h, {"fp32": 0, "bf16x9": 1}[math]))
+        return self
+
+    @property
+    def math(self):
+        return ("fp32", "bf16x9")[int(self._lib.sss_encoder_get_math(self._h))]
+
     def eval(self):
         return self
 

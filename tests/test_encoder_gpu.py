@@ -57,6 +57,33 @@ def test_encoder_larger_batch_against_oracle():
     assert out.shape == (200, out_dim)
 
 
+def test_encoder_bf16x9_tensor_core_linears_match_fp32():
+    """optional arithmetic of the dense linears: cuBLAS' fp32 emulation on the bf16 tensor cores must stay inside
+    the same tolerance against the oracle as the pedantic fp32 path (skipped when the loaded cuBLAS lacks it)"""
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from sessionsimilaritysearch_b200 import graph, sessions
+    in_dim, hidden, n_layers, out_dim, msl = 768, 800, 3, 1600, 20
+    _, graphs = ec.make_graphs(40, in_dim, 5, sessions.sequence_to_graph)
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 5)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    data = graph.collate(graphs).to("cuda")
+    assert enc.math == "fp32"
+    out32 = enc(data).cpu().numpy()
+    try:
+        enc.set_math("bf16x9")
+    except RuntimeError as e:
+        pytest.skip(str(e))
+    assert enc.math == "bf16x9"
+    out9 = enc(data).cpu().numpy()
+    ref = eo.encoder_forward(P, eo.batch_from_pyg(graph.collate(graphs)), n_layers).numpy()
+    scale = float(np.abs(ref).max())
+    np.testing.assert_allclose(out9, ref, rtol=3e-4, atol=3e-4 * scale)
+    np.testing.assert_allclose(out9, out32, rtol=3e-4, atol=3e-4 * scale)
+    enc.set_math("fp32")
+    assert np.array_equal(enc(data).cpu().numpy(), out32)
+
+
 def test_nan_input_raises_like_the_reference():
     import sessionsimilaritysearch_b200 as sss
     from sessionsimilaritysearch_b200 import graph, sessions

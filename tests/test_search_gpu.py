@@ -231,6 +231,49 @@ def test_wide_rows_take_the_kloop_tensor_path(sss, oracle, d, n, nq):
     assert recall >= 0.97 and np.max(np.abs(Db - D)) <= 3e-3, recall
 
 
+@pytest.mark.parametrize("case", ["ties", "ties_sessions", "long_sessions", "k256", "k300"])
+def test_lazy_rescoring_edge_cases_at_bootstrap_size(sss, oracle, case):
+    """Indexes of >= 262144 rows take the bootstrapped schedule, where exact mode keeps candidate ROWS with their
+    tensor-core keys between waves and re-scores once at the end (lazy; k <= 256).  Tie-heavy data (the margin band
+    holds far more than k sessions -> the query falls back to per-wave re-scoring), sessions longer than a chunk,
+    and both sides of the k limit must all stay bit-identical to the fp32 mode (pinned to the oracle elsewhere)."""
+    n, d, k, seg = 300000, 64, 100, None
+    if case.startswith("ties"):
+        db = make_ties(n, d, 41)
+        q = make_ties(70, d, 42)
+        metric = 'ip'
+        if case == "ties_sessions":
+            seg = make_segments(n, 43)
+    elif case == "long_sessions":
+        seg = make_segments(n, 44, mean=40)
+        db = make_session_rows(seg, d, 45, noise=0.2)
+        q = make_iid(70, d, 46)
+        metric = 'cos'
+    else:
+        seg = make_segments(n, 47)
+        db = make_session_rows(seg, d, 48)
+        q = make_iid(70, d, 49)
+        metric = 'cos'
+        k = 256 if case == "k256" else 300
+    ix = sss.build_index(db, metric, mode="exact")
+    if seg is not None:
+        ix.set_segments(seg, "max")
+    qq = sss.normalize(q) if metric == 'cos' else q
+    D, I = ix.search(qq, k)
+    st = ix.stats()
+    D2, I2 = ix.search(qq, k, mode="fp32")
+    _assert_exact(D, I, D2, I2)
+    assert st["scan_variant"] in ("ts", "2cta"), st
+    if case in ("k256", "k300"):
+        assert st["reruns"] == 0, st
+    print(case, {k: st[k] for k in ("waves", "reruns", "overflow_reason", "scan_variant")})
+    sub = np.array([0, 33, 69])
+    dbn = oracle.normalize(db, oracle.NORM_UTIL) if metric == 'cos' else db
+    qn = oracle.normalize(q[sub], oracle.NORM_UTIL) if metric == 'cos' else q[sub]
+    Do, Io = oracle.search_flat(dbn, qn, k, seg_off=seg, reduce=1 if seg is not None else 0)
+    _assert_exact(D[sub], I[sub], Do, Io)
+
+
 def test_torch_device_tensors(sss, oracle):
     import torch
     db = make_iid(10000, 128, 21)
