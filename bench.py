@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--shard", default=None,
+                    help="diagnostics: R/W = build and search only shard R of a W-way row sharding on ONE GPU (no collective)")
     return ap.parse_args()
 
 
@@ -170,7 +172,7 @@ def run_reference(a):
                                    % (sample, a.rows, dt)},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
@@ -229,8 +231,31 @@ def workload_config(a):
             "l2": "inputs larger than L2 (database %.2f GB bf16 per pass)" % (a.rows * a.d * 2 / 1e9)}
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner, cuBLAS or
+    driver notices) is sent to stderr; emit() writes the line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     a = parse()
+    quiet_stdout()
     if a.impl == "reference":
         return run_reference(a)
     import torch
@@ -249,12 +274,13 @@ def main():
     # ---- synthetic database, generated on the device shard by shard -------------------------------
     lens_all = session_lengths(a.rows, 1234)
     n_sess_all = len(lens_all)
-    s_lo = n_sess_all * rank // world
-    s_hi = n_sess_all * (rank + 1) // world
+    shard_r, shard_w = (int(x) for x in a.shard.split("/")) if a.shard else (rank, world)
+    s_lo = n_sess_all * shard_r // shard_w
+    s_hi = n_sess_all * (shard_r + 1) // shard_w
     lens = lens_all[s_lo:s_hi]
     row_off = int(lens_all[:s_lo].sum())
     g = torch.Generator(device=dev)
-    g.manual_seed(4321 + rank)
+    g.manual_seed(4321 + shard_r)
     inner = sss.IndexFlatIP(a.d, device=local_rank, id_offset=(s_lo if a.reduce != "none" else row_off), mode=a.mode)
     lens_t = torch.from_numpy(lens).to(dev)
     host_rows = []
@@ -281,6 +307,11 @@ def main():
     gq.manual_seed(99)  # same queries on every rank
     if world > 1:
         dist.broadcast(base_for_q, src=0)
+    elif a.shard and shard_r != 0:  # the sharded run's queries come from rank 0's first sessions: regenerate those
+        g0 = torch.Generator(device=dev)
+        g0.manual_seed(4321)
+        n0 = min(chunk, n_sess_all // shard_w)
+        base_for_q = torch.randn((n0, a.d), generator=g0, device=dev)[:8192].clone()
     pick = torch.randint(0, base_for_q.shape[0], (a.nq,), generator=gq, device=dev)
     q_dev = sss.normalize(base_for_q[pick] + 0.3 * torch.randn((a.nq, a.d), generator=gq, device=dev))
     q_host = torch.empty((a.nq, a.d), dtype=torch.float32).pin_memory()
@@ -303,8 +334,13 @@ def main():
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            every = torch.empty(world, device=dev)
+            dist.all_gather_into_tensor(every, ms)
+            per_rank_ms.append([round(float(x) / steps, 4) for x in every])
+            ms = every.max()
         return float(ms.item())
+
+    per_rank_ms = []  # ms per step of every rank, one list per timed region (diagnostics: which rank sets the max)
 
     def step_dev():
         return index.search(q_dev, a.k)
@@ -334,6 +370,10 @@ def main():
     waves = inner.stats()["waves"]
     reruns = inner.stats()["reruns"]
     overflow_reason = inner.stats()["overflow_reason"]
+    if world > 1:  # a rerun on ANY rank sets the step time: report the maximum over ranks
+        t = torch.tensor([reruns, overflow_reason], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reruns, overflow_reason = int(t[0]), int(t[1])
     scan_kernel_name = {"ss": "scan_bf16_kernel", "ts": "scan_bf16_ts_kernel", "2cta": "scan_bf16_2cta_kernel",
                         "kloop": "scan_bf16_kloop_kernel", "fp32": "scan_fp32_kernel"}[inner.stats()["scan_variant"]]
     for _ in range(max(1, a.warmup // 2)):
@@ -454,10 +494,10 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "waves_per_step": waves, "overflow_reruns": reruns, "overflow_reason": overflow_reason, "refine_volumes_last_step": refine_stats,
+        "waves_per_step": waves, "overflow_reruns": reruns, "overflow_reason": overflow_reason, "per_rank_ms_per_step": per_rank_ms, "refine_volumes_last_step": refine_stats,
         "extra": extra,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

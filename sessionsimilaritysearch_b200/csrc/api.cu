@@ -164,6 +164,7 @@ struct sss_index {
   int device = 0, d = 0, d_pad = 0, metric = 0, num_sms = 148;
   int64_t id_offset = 0;
   bool tensor_ok = false;
+  int rec_boost = 1;  // 4 once a search overflowed a record sub-region (sticky: such data would do it again)
   RowStore rows;      // the added rows
   RowStore sums;      // per-segment sums (reduce == SUM)
   int reduce = 0;
@@ -422,7 +423,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   const bool overlap = tensor && ov && ov[0] == '1';
   if (tensor) {
     // leave shared memory for the refine blocks that co-run with the scan when overlapping
-    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan)) return 1;
+    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost)) return 1;
     if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
     ix->stat_variant = plan.kloop ? 4 : plan.two_cta ? 3 : plan.ts ? 2 : 1;
     if (overlap && !ix->side) {
@@ -435,7 +436,15 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     if (make_tensor_map_bf16_2d(tmap_q, ws.q_bf16, (uint64_t)nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
     if (make_tensor_map_bf16_2d(tmap_db, rs.bf16, (uint64_t)n_rows, (uint64_t)ix->d_pad, 128)) return 1;
   }
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  // Attempts: the normal schedule; if ONLY a record sub-region overflowed (a hot spot of one query inside one CTA's
+  // share of a wave), the same schedule again with 4x the records per sub-region (the index remembers that); anything
+  // else, or a second overflow, falls back to the safe schedule of 2048-row waves.
+  bool safe = false;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (tensor && plan.rec_cap != (plan.kloop ? 4 : 1) * kRecSubCap * ix->rec_boost) {
+      if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost)) return 1;
+      if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
+    }
     SelectState state = ws.state();
     state.cap = cap;
     if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr,
@@ -466,7 +475,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     const bool grouped = ix->reduce == SSS_REDUCE_MAX;
     const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
     const char* no_boot = getenv("SSS_NO_BOOTSTRAP");
-    const bool bootstrap = tensor && (plan.ts || plan.two_cta || plan.kloop) && attempt == 0 && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
+    const bool bootstrap = tensor && (plan.ts || plan.two_cta || plan.kloop) && !safe && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
                            (int64_t)(b.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4;
     if (bootstrap) {
       const size_t need = (size_t)n_boot_chunks * (size_t)nq_pad;
@@ -481,7 +490,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, b.nq, nq_pad, b.k, chunk_gap, 2.0f, state, st)) return 1;
       ix->stat_kernels += 2;
     }
-    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, attempt == 1, grouped, bootstrap ? kBootRows : 0, tensor && plan.total_mtiles == 1);
+    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, safe, grouped, bootstrap ? kBootRows : 0, tensor && plan.total_mtiles == 1);
     int64_t begin = 0;
     uint32_t wave_id = 0;
     const char* nl_env = getenv("SSS_NO_LAZY");  // A/B switch: exact re-scoring in every wave
@@ -511,13 +520,13 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.rec_cnt = cnt_buf;
       ra.rec_nsub = tensor ? plan.rec_nsub : 0;
       ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
-      ra.lazy = (mode == SSS_MODE_EXACT && attempt == 0 && b.k <= 256 && !no_lazy) ? 1 : 0;
+      ra.lazy = (mode == SSS_MODE_EXACT && !safe && b.k <= 256 && !no_lazy) ? 1 : 0;
       ra.final = end == ends.back() ? 1 : 0;
       ra.row_limit = n_rows;
       // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
       // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever
       // rise, and refine re-filters every record against the current threshold, so this is still exact).
-      const bool late = overlap && attempt == 0 && wave_tensor && prev_tensor && end - begin >= 524288;
+      const bool late = overlap && !safe && wave_tensor && prev_tensor && end - begin >= 524288;
       if (overlap) {
         if (w >= 3) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf], 0));                 // records[buf] are free
         if (w >= 2 && !late) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf ^ 1], 0));    // fresh thresholds
@@ -573,9 +582,13 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     if (flags[0] == 0) return 0;
     // a candidate list or record region overflowed (adversarial score order): redo with waves that
     // cannot overflow by construction
-    SSS_REQUIRE(attempt == 0, "candidate overflow persisted in the safe wave schedule (internal error)");
+    SSS_REQUIRE(!safe, "candidate overflow persisted in the safe wave schedule (internal error)");
     ix->stat_reruns += 1;
     ix->stat_overflow_reason = flags[0];
+    if (tensor && flags[0] == 1 && ix->rec_boost == 1)
+      ix->rec_boost = 4;
+    else
+      safe = true;
   }
   return 0;
 }

@@ -39,7 +39,8 @@ struct Bf16ScanPlan {
   bool kloop;       // wide rows (d_pad > 128): both operands streamed per K block, one query group per CTA pair
   int groups;       // K-loop variant: query groups of 256
 };
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan);
+// rec_boost multiplies the records per sub-region (1, or 4 after a search that overflowed one)
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost = 1);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,

@@ -181,6 +181,7 @@ struct ScanParams {
   int groups;            // K-loop variant: query groups of 256 (one per CTA pair)
 };
 
+template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  const ScanParams p) {
@@ -305,7 +306,7 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t qidx = (uint32_t)((mt_base + mt) * kTileQ + quarter * 32 + lane);
       const float thr = p.st.thr[qidx];
       const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * kTileRows);
-      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * kRecSubCap;
+      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * (size_t)kCap;
       mt += 2;
       while (mt >= num_mt) { mt -= num_mt; ++it; }
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 105);
@@ -328,7 +329,7 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (__any_sync(0xffffffffu, hit)) {
           if (hit) {
             const uint32_t idx = cur_mt == 0 ? rc0 : cur_mt == 1 ? rc1 : cur_mt == 2 ? rc2 : rc3;
-            if (idx < (uint32_t)kRecSubCap) {
+            if (idx < (uint32_t)kCap) {
               uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
               dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
 #pragma unroll
@@ -378,6 +379,7 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // TMEM: [0, a_cols) = A (num_mt * num_kb * 32 columns: lane = query, column = two bf16), then two 128-column
 // accumulator slots (slot == epilogue warpgroup).
 // ---------------------------------------------------------------------------------------------------------
+template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -538,7 +540,7 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
       const uint32_t qidx = (uint32_t)((mt_base + mt) * kTileQ + quarter * 32 + lane);
       const float thr = p.st.thr[qidx];
       const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * kTileRows);
-      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * kRecSubCap;
+      HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * (size_t)kCap;
       mt += 2;
       while (mt >= num_mt) { mt -= num_mt; ++it; }
       const long long e0 = clock64();
@@ -567,7 +569,7 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
         if (__any_sync(0xffffffffu, hit)) {
           if (hit) {
             const uint32_t idx = cur_mt == 0 ? rc0 : cur_mt == 1 ? rc1 : cur_mt == 2 ? rc2 : rc3;
-            if (idx < (uint32_t)kRecSubCap) {
+            if (idx < (uint32_t)kCap) {
               uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
               dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
 #pragma unroll
@@ -675,6 +677,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
       : "memory");
 }
 
+template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                       const ScanParams p) {
@@ -812,7 +815,7 @@ scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const bool q_ok = qidx < (uint32_t)nq_pad;
       const float thr = q_ok ? p.st.thr[qidx] : INFINITY;
       const uint32_t row_tile = (uint32_t)((int)p.row_begin + tile * 256);
-      HitRecord* myrec = p.rec + ((size_t)(q_ok ? qidx : 0u) * sub_stride + my_sub) * kRecSubCap;
+      HitRecord* myrec = p.rec + ((size_t)(q_ok ? qidx : 0u) * sub_stride + my_sub) * (size_t)kCap;
       j += 2;
       while (j >= num_j) { j -= num_j; ++it; }
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 305);
@@ -841,7 +844,7 @@ scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         if (__any_sync(0xffffffffu, hit)) {
           if (hit) {
             const uint32_t idx = cur_j == 0 ? rc0 : cur_j == 1 ? rc1 : cur_j == 2 ? rc2 : rc3;
-            if (idx < (uint32_t)kRecSubCap) {
+            if (idx < (uint32_t)kCap) {
               uint4* dst = reinterpret_cast<uint4*>(myrec + idx);
               dst[0] = make_uint4(qidx, row_tile + (uint32_t)(c * 32), 0u, 0u);
 #pragma unroll
@@ -1123,7 +1126,7 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
   return 0;
 }
 
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan) {
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost) {
   SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 4096, "tensor-core scan supports d <= 4096");
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
@@ -1150,7 +1153,7 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
     SSS_REQUIRE(stages >= 2, "not enough shared memory for the operand ring");
     plan->num_stages = stages;
     plan->smem_bytes = 1024 + stages * kKloopStageBytes + kBarrierBytes;
-    plan->rec_cap = 4 * kRecSubCap;  // a query has ppg * 2 sub-regions here, a quarter of the d <= 128 kernels'
+    plan->rec_cap = 4 * kRecSubCap * rec_boost;  // a query has ppg * 2 sub-regions here, a quarter of the d <= 128 kernels'
     plan->rec_nsub = ppg * 2;
     plan->n_regions = (int)nq_pad * plan->rec_nsub;
     plan->tile_rows = 512;
@@ -1189,7 +1192,7 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
     SSS_REQUIRE(stages2 >= 2, "not enough shared memory for the DB tile ring");
     plan->num_stages = stages2;
     plan->smem_bytes = 1024 + q_bytes2 + stages2 * stage_bytes2 + kBarrierBytes;
-    plan->rec_cap = kRecSubCap;
+    plan->rec_cap = kRecSubCap * rec_boost;
     plan->rec_nsub = pairs * 2;
     plan->n_regions = (int)nq_pad * plan->rec_nsub;
     plan->tile_rows = 256;
@@ -1205,7 +1208,7 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   SSS_REQUIRE(stages >= 2, "not enough shared memory for the DB tile ring");
   plan->num_stages = stages;
   plan->smem_bytes = 1024 + q_bytes + stages * stage_bytes + kBarrierBytes;
-  plan->rec_cap = kRecSubCap;
+  plan->rec_cap = kRecSubCap * rec_boost;
   plan->rec_nsub = plan->grid_x * 2;
   plan->n_regions = (int)nq_pad * plan->rec_nsub;
   return 0;
@@ -1248,18 +1251,23 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
     }
   }
   if (p.n_tiles <= 0) return 0;
+  const bool big = plan.rec_cap != kRecSubCap && !plan.kloop;  // boosted sub-regions (after an overflow): 4x
+  SSS_REQUIRE(plan.kloop || plan.rec_cap == kRecSubCap || plan.rec_cap == 4 * kRecSubCap, "unsupported record capacity");
   static int smem_set = 0;
   if (smem_set < plan.smem_bytes) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     plan.smem_bytes));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     plan.smem_bytes));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kloop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     plan.smem_bytes));
-    smem_set = plan.smem_bytes;
+    const int sb = plan.smem_bytes;
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kloop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    smem_set = sb;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
+  const CUtensorMap& mq = *(const CUtensorMap*)tmap_q;
+  const CUtensorMap& mdb = *(const CUtensorMap*)tmap_db;
   if (plan.two_cta || plan.kloop) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -1274,16 +1282,22 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (plan.kloop)
-      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_kloop_kernel, *(const CUtensorMap*)tmap_q,
-                                     *(const CUtensorMap*)tmap_db, p));
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_kloop_kernel, mq, mdb, p));
+    else if (big)
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<4 * kRecSubCap>, mq, mdb, p));
     else
-      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel, *(const CUtensorMap*)tmap_q,
-                                     *(const CUtensorMap*)tmap_db, p));
-  } else if (plan.ts)
-    scan_bf16_ts_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_db, p);
-  else
-    scan_bf16_kernel<<<grid, kNumThreads, plan.smem_bytes, stream>>>(*(const CUtensorMap*)tmap_q,
-                                                                     *(const CUtensorMap*)tmap_db, p);
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<kRecSubCap>, mq, mdb, p));
+  } else if (plan.ts) {
+    if (big)
+      scan_bf16_ts_kernel<4 * kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+    else
+      scan_bf16_ts_kernel<kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+  } else {
+    if (big)
+      scan_bf16_kernel<4 * kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mq, mdb, p);
+    else
+      scan_bf16_kernel<kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mq, mdb, p);
+  }
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

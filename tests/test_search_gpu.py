@@ -274,6 +274,31 @@ def test_lazy_rescoring_edge_cases_at_bootstrap_size(sss, oracle, case):
     _assert_exact(D[sub], I[sub], Do, Io)
 
 
+def test_full_record_subregion_retries_with_more_room_not_the_safe_schedule(sss, oracle):
+    """Three 256-row tiles of near-duplicates of one query, 74 tiles apart inside the second wave, land in the same
+    (query, CTA pair, warpgroup) record sub-region: 24 hit records against its 16.  The search is redone once with
+    4x the records per sub-region (same wave schedule, not the 2048-row safe schedule), the index remembers it,
+    and the result is exact."""
+    n, d, nq = 300000, 128, 300
+    db = make_iid(n, d, 51)
+    q = make_iid(nq, d, 52)
+    rng = np.random.default_rng(53)
+    for t in (600, 674, 748):
+        rows = slice(t * 256, (t + 1) * 256)
+        db[rows] = 40.0 * q[5] + rng.standard_normal((256, d)).astype(np.float32)
+    ix = sss.build_index(db, 'cos', mode="exact")
+    qn = sss.normalize(q)
+    D, I = ix.search(qn, 100)
+    st = ix.stats()
+    assert st["scan_variant"] == "2cta" and st["reruns"] == 1 and st["overflow_reason"] == 1 and st["waves"] <= 8, st
+    D2, I2 = ix.search(qn, 100, mode="fp32")
+    _assert_exact(D, I, D2, I2)
+    assert np.all((I[5] // 256 == 600) | (I[5] // 256 == 674) | (I[5] // 256 == 748))
+    D3, I3 = ix.search(qn, 100)
+    assert ix.stats()["reruns"] == 0          # the larger sub-regions are kept for this index
+    _assert_exact(D3, I3, D2, I2)
+
+
 def test_torch_device_tensors(sss, oracle):
     import torch
     db = make_iid(10000, 128, 21)
