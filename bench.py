@@ -213,6 +213,25 @@ def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
         out["encoder_bf16x9_sessions_per_s"] = n_sessions / (e0.elapsed_time(e1) * 1e-3)
     except RuntimeError as e:
         out["encoder_bf16x9_sessions_per_s"] = "unavailable: %s" % str(e)[:80]
+    # host featuriser: the reference's per-session Python (mirrored by sessions.sequence_to_graph + graph.collate)
+    # against the native batched sss_featurize_batch on the same sessions
+    from sessionsimilaritysearch_b200 import featurize
+    sess_all = synth.make_sessions(n_sessions, 17)
+    tok = synth.HashTokenizer()
+    t0 = time.perf_counter()
+    for i in range(0, 200, 200):
+        graph.collate([sessions.sequence_to_graph(0, s, s[:1], tok, 20) for s in sess_all[i:i + 200]])
+    out["featurizer_python_sessions_per_s"] = 200 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    vocab = featurize.QueryVocab()
+    flat = featurize.flatten(sess_all, vocab)
+    t1 = time.perf_counter()
+    for i in range(0, n_sessions, batch):
+        featurize.featurize_arrays(flat.slice(i, min(n_sessions, i + batch)))
+    t2 = time.perf_counter()
+    out["featurizer_native_sessions_per_s"] = n_sessions / (t2 - t0)
+    out["featurizer_native_split"] = "flatten (python) %.1f us + native %.1f us per session" % (
+        (t1 - t0) / n_sessions * 1e6, (t2 - t1) / n_sessions * 1e6)
     if not no_cpu:
         from oracle import encoder_oracle as eo
         cb = eo.batch_from_pyg(graph.collate(graphs[:batch]))

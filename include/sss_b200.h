@@ -187,6 +187,45 @@ enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1 };
 int sss_encoder_set_math(sss_encoder_t* enc, int math);
 int sss_encoder_get_math(const sss_encoder_t* enc);
 
+/* ---- batched host featuriser (replaces the per-session Python of sequence_to_graph, util_amazon_filtered.py:98-230,
+ * followed by PyG's Batch.from_data_list, test_amazon_filterd.py:485-488, for what the encoder reads) ---------- */
+
+/* Sessions as flat HOST arrays.  An action is a search (act_is_search = 1, act_key = the caller's id of the query
+ * string: the row of its text feature) or an item event (0, act_key = item id, the last field of the reference's
+ * action tuple).  uniq_items lists every session's distinct item ids in node order — the reference takes
+ * list(set(ids)), so the Python caller passes exactly that. */
+typedef struct sss_flat_sessions {
+  int64_t n_sessions;
+  const int64_t* act_off;        /* [n_sessions + 1] */
+  const uint8_t* act_is_search;  /* [n_actions] */
+  const int64_t* act_key;        /* [n_actions] */
+  const int64_t* uniq_off;       /* [n_sessions + 1] */
+  const int64_t* uniq_items;     /* [sum of distinct items] */
+} sss_flat_sessions_t;
+
+/* Output: the batch-level arrays of sss_graph_batch_t (indices already batch-global), HOST buffers with the
+ * capacities cap_* (sss_featurize_sizes gives the exact sizes).  pp_weight and last_click_mask may be NULL. */
+typedef struct sss_graph_arrays {
+  int64_t cap_query, cap_product, cap_expanded, cap_qp, cap_pp;
+  int64_t n_query, n_product, n_expanded, e_qp, e_pp;  /* filled */
+  int64_t* query_key;      /* [n_query] text key of the node (root_query_key for node 0 of every session) */
+  int64_t* query_pos;      /* [n_query] pos_emb_id */
+  int64_t* query_batch;    /* [n_query] session index */
+  int64_t* product_key;    /* [n_product] item id (0 = the placeholder of an item-less session) */
+  int64_t* product_cnt;    /* [n_product] */
+  int64_t* product_batch;  /* [n_product] */
+  int64_t* product_pos;    /* [n_expanded] pos_emb_id of every occurrence, grouped by product */
+  int64_t* qp_src; int64_t* qp_dst;   /* [e_qp] ('query','clicks','product'); its transpose is 'clicked by' */
+  int64_t* pp_src; int64_t* pp_dst;   /* [e_pp] ('product','to','product'), de-duplicated */
+  float* pp_weight;                   /* [e_pp] multiplicity of the transition */
+  float* last_click_mask;             /* [n_product] */
+} sss_graph_arrays_t;
+
+int sss_featurize_sizes(const sss_flat_sessions_t* s, int64_t* n_query, int64_t* n_product, int64_t* n_expanded,
+                        int64_t* e_qp, int64_t* e_pp);
+/* n_threads <= 0: all hardware threads (sessions are independent). */
+int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, sss_graph_arrays_t* out, int n_threads);
+
 /* BinarizeHead eval forward, mlp=None (model/model.py:117-138): out = sign(x W^T + b) in {-1,0,+1}.
  * x [n, in], W [out, in], b [out], out [n, out]; device pointers. */
 int sss_binarize_head(const float* x, const float* W, const float* b, int64_t n, int in_dim, int out_dim,

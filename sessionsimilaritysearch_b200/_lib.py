@@ -29,6 +29,20 @@ class GraphBatch(ctypes.Structure):
                 ("e_pp", c_i64), ("pp_src", c_vp), ("pp_dst", c_vp)]
 
 
+class FlatSessions(ctypes.Structure):
+    _fields_ = [("n_sessions", c_i64), ("act_off", c_vp), ("act_is_search", c_vp), ("act_key", c_vp),
+                ("uniq_off", c_vp), ("uniq_items", c_vp)]
+
+
+class GraphArrays(ctypes.Structure):
+    _fields_ = [("cap_query", c_i64), ("cap_product", c_i64), ("cap_expanded", c_i64), ("cap_qp", c_i64),
+                ("cap_pp", c_i64), ("n_query", c_i64), ("n_product", c_i64), ("n_expanded", c_i64), ("e_qp", c_i64),
+                ("e_pp", c_i64), ("query_key", c_vp), ("query_pos", c_vp), ("query_batch", c_vp),
+                ("product_key", c_vp), ("product_cnt", c_vp), ("product_batch", c_vp), ("product_pos", c_vp),
+                ("qp_src", c_vp), ("qp_dst", c_vp), ("pp_src", c_vp), ("pp_dst", c_vp), ("pp_weight", c_vp),
+                ("last_click_mask", c_vp)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/sss_b200.h
 SIGNATURES = {
     "sss_last_error": (ctypes.c_char_p, []),
@@ -56,6 +70,9 @@ SIGNATURES = {
     "sss_encoder_destroy": (c_int, [c_vp]),
     "sss_encoder_set_param": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_int, c_vp]),
     "sss_encoder_forward": (c_int, [c_vp, ctypes.POINTER(GraphBatch), c_vp, c_vp, c_vp]),
+    "sss_featurize_sizes": (c_int, [ctypes.POINTER(FlatSessions), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "sss_featurize_batch": (c_int, [ctypes.POINTER(FlatSessions), c_i64, ctypes.POINTER(GraphArrays), c_int]),
     "sss_encoder_set_math": (c_int, [c_vp, c_int]),
     "sss_encoder_get_math": (c_int, [c_vp]),
     "sss_binarize_head": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp]),

@@ -1,0 +1,217 @@
+// featurize.cu — batched HOST featuriser (no device code): flattened session actions -> the integer arrays the
+// encoder reads from a batch of session graphs.  It replaces the per-session Python of the reference's
+// sequence_to_graph (util_amazon_filtered.py:98-230 with helpers :7-22, :75-83) followed by PyG's
+// Batch.from_data_list (test_amazon_filterd.py:485-488) for everything the encoder consumes: node order, positions,
+// counts, the three edge lists with batch-global indices, transition multiplicities and the last-click mask.
+// Text is not touched here: a node carries the KEY of its text (the caller's id of the query string, or the item
+// id), and the features are gathered from a cache on the device.
+//
+// Layout rules restated from the reference (same as sessionsimilaritysearch_b200/sessions.py, the Python mirror):
+//   query nodes    node 0 = empty-string root (pos = len), then one per search at position i (pos = len - (i + 1))
+//   product nodes  the session's distinct items in the order the caller gives (the reference: list(set(ids)));
+//                  cnt = occurrences; pos = len - j for every occurrence j, grouped by product;
+//                  an item-less session gets one node (item 0, cnt 1, pos 0)
+//   q -> p edges   one per item event, from the latest search node (root before the first search); multi-edges kept
+//   p -> p edges   consecutive item transitions, de-duplicated in first-appearance order with their multiplicity;
+//                  self transitions kept
+//   last click     destination of the last transition (node 0 when there is none)
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sss_b200.h"
+#include "common.cuh"
+
+namespace {
+
+struct Counts {
+  int64_t nq = 0, np = 0, ne = 0, eqp = 0, epp = 0;
+};
+
+inline int slot_of(const int64_t* uniq, int n_uniq, int64_t item) {
+  for (int i = 0; i < n_uniq; ++i)
+    if (uniq[i] == item) return i;
+  return -1;
+}
+
+// distinct consecutive transitions of one session, first-appearance order; returns their number
+inline int transitions(const sss_flat_sessions_t* s, int64_t sess, std::vector<int>& chain, std::vector<int>& pa,
+                       std::vector<int>& pb, std::vector<int>& pw, bool* bad) {
+  const int64_t a0 = s->act_off[sess], a1 = s->act_off[sess + 1];
+  const int64_t* uniq = s->uniq_items + s->uniq_off[sess];
+  const int n_uniq = (int)(s->uniq_off[sess + 1] - s->uniq_off[sess]);
+  chain.clear();
+  pa.clear();
+  pb.clear();
+  pw.clear();
+  for (int64_t a = a0; a < a1; ++a)
+    if (!s->act_is_search[a]) {
+      const int sl = slot_of(uniq, n_uniq, s->act_key[a]);
+      if (sl < 0) {
+        *bad = true;
+        return 0;
+      }
+      chain.push_back(sl);
+    }
+  for (size_t i = 0; i + 1 < chain.size(); ++i) {
+    const int x = chain[i], y = chain[i + 1];
+    size_t j = 0;
+    for (; j < pa.size(); ++j)
+      if (pa[j] == x && pb[j] == y) break;
+    if (j == pa.size()) {
+      pa.push_back(x);
+      pb.push_back(y);
+      pw.push_back(1);
+    } else {
+      pw[j] += 1;
+    }
+  }
+  return (int)pa.size();
+}
+
+int count_session(const sss_flat_sessions_t* s, int64_t sess, Counts* c, std::vector<int>& chain, std::vector<int>& pa,
+                  std::vector<int>& pb, std::vector<int>& pw) {
+  const int64_t a0 = s->act_off[sess], a1 = s->act_off[sess + 1];
+  int64_t searches = 0, items = 0;
+  for (int64_t a = a0; a < a1; ++a) (s->act_is_search[a] ? searches : items) += 1;
+  const int64_t n_uniq = s->uniq_off[sess + 1] - s->uniq_off[sess];
+  if ((items == 0) != (n_uniq == 0)) return 1;
+  bool bad = false;
+  c->nq = 1 + searches;
+  c->np = n_uniq > 0 ? n_uniq : 1;
+  c->ne = items > 0 ? items : 1;
+  c->eqp = items;
+  c->epp = transitions(s, sess, chain, pa, pb, pw, &bad);
+  return bad ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int sss_featurize_sizes(const sss_flat_sessions_t* s, int64_t* n_query, int64_t* n_product,
+                                   int64_t* n_expanded, int64_t* e_qp, int64_t* e_pp) {
+  SSS_REQUIRE(s && s->n_sessions >= 0 && (s->n_sessions == 0 || (s->act_off && s->uniq_off)),
+              "sss_featurize_sizes: bad argument");
+  Counts tot;
+  std::vector<int> chain, pa, pb, pw;
+  for (int64_t i = 0; i < s->n_sessions; ++i) {
+    Counts c;
+    SSS_REQUIRE(count_session(s, i, &c, chain, pa, pb, pw) == 0,
+                "sss_featurize: the distinct-item list of session " + std::to_string(i) +
+                    " does not match its item events");
+    tot.nq += c.nq; tot.np += c.np; tot.ne += c.ne; tot.eqp += c.eqp; tot.epp += c.epp;
+  }
+  if (n_query) *n_query = tot.nq;
+  if (n_product) *n_product = tot.np;
+  if (n_expanded) *n_expanded = tot.ne;
+  if (e_qp) *e_qp = tot.eqp;
+  if (e_pp) *e_pp = tot.epp;
+  return 0;
+}
+
+extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, sss_graph_arrays_t* out,
+                                   int n_threads) {
+  SSS_REQUIRE(s && out && s->n_sessions >= 0, "sss_featurize_batch: bad argument");
+  const int64_t n = s->n_sessions;
+  // pass 1: per-session sizes -> offsets
+  std::vector<Counts> off((size_t)n + 1);
+  {
+    std::vector<int> chain, pa, pb, pw;
+    Counts run;
+    for (int64_t i = 0; i < n; ++i) {
+      Counts c;
+      SSS_REQUIRE(count_session(s, i, &c, chain, pa, pb, pw) == 0,
+                  "sss_featurize: the distinct-item list of session " + std::to_string(i) +
+                      " does not match its item events");
+      off[(size_t)i] = run;
+      run.nq += c.nq; run.np += c.np; run.ne += c.ne; run.eqp += c.eqp; run.epp += c.epp;
+    }
+    off[(size_t)n] = run;
+  }
+  const Counts& tot = off[(size_t)n];
+  SSS_REQUIRE(out->cap_query >= tot.nq && out->cap_product >= tot.np && out->cap_expanded >= tot.ne &&
+                  out->cap_qp >= tot.eqp && out->cap_pp >= tot.epp,
+              "sss_featurize_batch: output capacity too small (use sss_featurize_sizes)");
+  out->n_query = tot.nq; out->n_product = tot.np; out->n_expanded = tot.ne; out->e_qp = tot.eqp; out->e_pp = tot.epp;
+
+  // pass 2: fill (sessions are independent: split them over threads)
+  auto fill = [&](int64_t lo, int64_t hi) {
+    std::vector<int> chain, pa, pb, pw;
+    std::vector<int64_t> occ;
+    for (int64_t i = lo; i < hi; ++i) {
+      const Counts& o = off[(size_t)i];
+      const int64_t a0 = s->act_off[i], a1 = s->act_off[i + 1];
+      const int64_t len = a1 - a0;
+      const int64_t* uniq = s->uniq_items + s->uniq_off[i];
+      const int n_uniq = (int)(s->uniq_off[i + 1] - s->uniq_off[i]);
+      // query nodes + q -> p edges
+      int64_t q = o.nq, eq = o.eqp;
+      out->query_key[q] = root_query_key;
+      out->query_pos[q] = len;
+      out->query_batch[q] = i;
+      ++q;
+      int64_t cur = 0;
+      for (int64_t a = a0; a < a1; ++a) {
+        if (s->act_is_search[a]) {
+          out->query_key[q] = s->act_key[a];
+          out->query_pos[q] = len - (a - a0 + 1);
+          out->query_batch[q] = i;
+          ++q;
+          ++cur;
+        } else {
+          out->qp_src[eq] = o.nq + cur;
+          out->qp_dst[eq] = o.np + slot_of(uniq, n_uniq, s->act_key[a]);
+          ++eq;
+        }
+      }
+      // product nodes, counts, positions grouped by product
+      int64_t e = o.ne;
+      if (n_uniq == 0) {
+        out->product_key[o.np] = 0;
+        out->product_cnt[o.np] = 1;
+        out->product_batch[o.np] = i;
+        out->product_pos[e] = 0;
+        if (out->last_click_mask) out->last_click_mask[o.np] = 1.0f;
+      } else {
+        for (int u = 0; u < n_uniq; ++u) {
+          int64_t cnt = 0;
+          for (int64_t a = a0; a < a1; ++a)
+            if (!s->act_is_search[a] && s->act_key[a] == uniq[u]) {
+              out->product_pos[e++] = len - (a - a0);
+              ++cnt;
+            }
+          out->product_key[o.np + u] = uniq[u];
+          out->product_cnt[o.np + u] = cnt;
+          out->product_batch[o.np + u] = i;
+          if (out->last_click_mask) out->last_click_mask[o.np + u] = 0.0f;
+        }
+      }
+      // p -> p transitions
+      bool bad = false;
+      const int np_pairs = transitions(s, i, chain, pa, pb, pw, &bad);
+      for (int j = 0; j < np_pairs; ++j) {
+        out->pp_src[o.epp + j] = o.np + pa[(size_t)j];
+        out->pp_dst[o.epp + j] = o.np + pb[(size_t)j];
+        if (out->pp_weight) out->pp_weight[o.epp + j] = (float)pw[(size_t)j];
+      }
+      if (out->last_click_mask && n_uniq > 0)
+        out->last_click_mask[o.np + (chain.size() >= 2 ? chain.back() : 0)] = 1.0f;
+    }
+  };
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (n < 4096 || nt == 1) {
+    fill(0, n);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t lo = t * per, hi = std::min<int64_t>(n, lo + per);
+      if (lo < hi) th.emplace_back(fill, lo, hi);
+    }
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}

@@ -1,0 +1,157 @@
+"""Batched featuriser: many sessions -> ONE encoder-ready batch, through the native sss_featurize_batch (C ABI).
+
+The reference builds one PyG HeteroData per session in Python (util_amazon_filtered.py:98-230: four or five HF
+tokenizer calls and a dozen small tensors each) and glues 200 of them with Batch.from_data_list
+(test_amazon_filterd.py:485-488); `sessions.sequence_to_graph` + `graph.collate` mirror that call for call (about
+2.2 ms per session on this image's host).  This module produces the same batch — the arrays the encoder reads,
+identical node order, positions, counts, edges — from flat integer arrays in native code, and takes the node TEXT
+from a feature cache keyed by query string / item id instead of tokenising it again (the text model is a pure function
+of the string: SURVEY.md 8a3, 8f rank 3).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .graph import EDGE_PP, EDGE_PQ, EDGE_QP, SessionBatch
+from .sessions import SEARCH
+
+
+class FlatSessions:
+    """sessions as flat numpy arrays (the input of the native featuriser)"""
+
+    def __init__(self, act_off, act_is_search, act_key, uniq_off, uniq_items):
+        self.act_off = np.ascontiguousarray(act_off, dtype=np.int64)
+        self.act_is_search = np.ascontiguousarray(act_is_search, dtype=np.uint8)
+        self.act_key = np.ascontiguousarray(act_key, dtype=np.int64)
+        self.uniq_off = np.ascontiguousarray(uniq_off, dtype=np.int64)
+        self.uniq_items = np.ascontiguousarray(uniq_items, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.act_off) - 1
+
+    def slice(self, lo, hi):
+        a0, a1 = int(self.act_off[lo]), int(self.act_off[hi])
+        u0, u1 = int(self.uniq_off[lo]), int(self.uniq_off[hi])
+        return FlatSessions(self.act_off[lo:hi + 1] - a0, self.act_is_search[a0:a1], self.act_key[a0:a1],
+                            self.uniq_off[lo:hi + 1] - u0, self.uniq_items[u0:u1])
+
+
+class QueryVocab:
+    """query string -> key (row of its text feature); key 0 is the empty string of every session's root node"""
+
+    def __init__(self):
+        self.ids = {"": 0}
+
+    def __call__(self, s):
+        s = "" if s is None else s
+        k = self.ids.get(s)
+        if k is None:
+            k = self.ids[s] = len(self.ids)
+        return k
+
+    def __len__(self):
+        return len(self.ids)
+
+
+def flatten(sessions, vocab, ignore_query=False):
+    """action tuples (ts, type, keyword, asin, ptype, brand, title, item_id) -> FlatSessions.
+    The distinct items of a session are taken as list(set(ids)), the node order of the reference
+    (util_amazon_filtered.py:128)."""
+    act_off, kinds, keys, uniq_off, uniq = [0], [], [], [0], []
+    for seq in sessions:
+        items = []
+        for act in seq:
+            if act[1] == SEARCH:
+                if ignore_query:
+                    continue
+                kinds.append(1)
+                keys.append(vocab(act[2]))
+            else:
+                kinds.append(0)
+                keys.append(act[-1])
+                items.append(act[-1])
+        act_off.append(len(kinds))
+        uniq.extend(set(items))
+        uniq_off.append(len(uniq))
+    return FlatSessions(act_off, kinds, keys, uniq_off, uniq)
+
+
+def featurize_arrays(flat, root_query_key=0, n_threads=0):
+    """native call: FlatSessions -> dict of numpy arrays (batch-global indices)"""
+    lib = _lib.load()
+    fs = _lib.FlatSessions(len(flat), flat.act_off.ctypes.data, flat.act_is_search.ctypes.data, flat.act_key.ctypes.data,
+                           flat.uniq_off.ctypes.data, flat.uniq_items.ctypes.data)
+    n = [ctypes.c_int64() for _ in range(5)]
+    check(lib.sss_featurize_sizes(ctypes.byref(fs), *[ctypes.byref(x) for x in n]))
+    nq, npr, ne, eqp, epp = (int(x.value) for x in n)
+    a = {"query_key": np.empty(nq, np.int64), "query_pos": np.empty(nq, np.int64), "query_batch": np.empty(nq, np.int64),
+         "product_key": np.empty(npr, np.int64), "product_cnt": np.empty(npr, np.int64),
+         "product_batch": np.empty(npr, np.int64), "product_pos": np.empty(ne, np.int64),
+         "qp_src": np.empty(eqp, np.int64), "qp_dst": np.empty(eqp, np.int64),
+         "pp_src": np.empty(epp, np.int64), "pp_dst": np.empty(epp, np.int64),
+         "pp_weight": np.empty(epp, np.float32), "last_click_mask": np.empty(npr, np.float32)}
+    ga = _lib.GraphArrays(nq, npr, ne, eqp, epp, 0, 0, 0, 0, 0,
+                          *[a[k].ctypes.data for k in ("query_key", "query_pos", "query_batch", "product_key",
+                                                       "product_cnt", "product_batch", "product_pos", "qp_src",
+                                                       "qp_dst", "pp_src", "pp_dst", "pp_weight", "last_click_mask")])
+    check(lib.sss_featurize_batch(ctypes.byref(fs), int(root_query_key), ctypes.byref(ga), int(n_threads)))
+    a["n_graphs"] = len(flat)
+    return a
+
+
+class FeatureCache:
+    """text features on the device, one row per query key and one per item id (what the reference's
+    PretrainedQAEAEncoder computes per node, model/NodeEmbedding.py:112-125, computed once per distinct string)"""
+
+    def __init__(self, query_features, item_ids, item_features, device):
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.device = dev
+        self.query_features = torch.as_tensor(query_features, dtype=torch.float32).to(dev)
+        ids = np.asarray(item_ids, dtype=np.int64)
+        self.item_features = torch.as_tensor(item_features, dtype=torch.float32).to(dev)
+        order = np.argsort(ids, kind="stable")
+        self._sorted_ids = ids[order]
+        self._rows = order
+
+    def item_rows(self, item_ids):
+        pos = np.searchsorted(self._sorted_ids, item_ids)
+        pos = np.minimum(pos, len(self._sorted_ids) - 1)
+        if not np.array_equal(self._sorted_ids[pos], item_ids):
+            raise KeyError("item id without a cached text feature")
+        return self._rows[pos]
+
+
+def featurize_batch(flat, cache, root_query_key=0, n_threads=0):
+    """FlatSessions -> SessionBatch on the cache's device, ready for SessionEncoder.__call__ (same attributes as
+    graph.collate([sequence_to_graph(...), ...]) with the text features already in place)."""
+    a = featurize_arrays(flat, root_query_key, n_threads)
+    dev = cache.device
+
+    def t(x):
+        return torch.from_numpy(x).to(dev, non_blocking=True)
+
+    out = SessionBatch()
+    out.num_graphs = a["n_graphs"]
+    q = out["query"]
+    q.x = cache.query_features.index_select(0, t(a["query_key"]))
+    q.pos_emb_id = t(a["query_pos"])
+    q.batch = t(a["query_batch"])
+    q.num_nodes = len(a["query_key"])
+    p = out["product"]
+    p.x = t(a["product_key"])
+    p.input_ids = cache.item_features.index_select(0, t(cache.item_rows(a["product_key"])))
+    p.cnt = t(a["product_cnt"])
+    p.pos_emb_id = t(a["product_pos"])
+    p.batch = t(a["product_batch"])
+    p.last_click_mask = t(a["last_click_mask"])
+    p.num_nodes = len(a["product_key"])
+    qp = torch.stack([t(a["qp_src"]), t(a["qp_dst"])])
+    out[EDGE_QP].edge_index = qp
+    out[EDGE_PQ].edge_index = qp.flip(0)
+    pp = out[EDGE_PP]
+    pp.edge_index = torch.stack([t(a["pp_src"]), t(a["pp_dst"])])
+    pp.edge_weight = t(a["pp_weight"])
+    return out

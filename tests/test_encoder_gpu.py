@@ -84,6 +84,40 @@ def test_encoder_bf16x9_tensor_core_linears_match_fp32():
     assert np.array_equal(enc(data).cpu().numpy(), out32)
 
 
+def test_native_featuriser_feeds_the_encoder_like_the_python_path():
+    """flatten -> sss_featurize_batch -> feature cache gather -> encoder must give the very same embeddings as
+    sequence_to_graph per session -> collate -> encoder (same node order, same features, same kernels)."""
+    import torch
+    import sessionsimilaritysearch_b200 as sss
+    from sessionsimilaritysearch_b200 import featurize, graph, sessions, synth
+    in_dim, hidden, n_layers, out_dim, msl = 48, 64, 3, 100, 20
+    sess, graphs = ec.make_graphs(300, in_dim, 23, sessions.sequence_to_graph)
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 23)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    tok = synth.HashTokenizer()
+
+    def feats(strings):
+        ids = tok(strings, padding='max_length', max_length=20, truncation=True, return_tensors="pt")['input_ids']
+        return synth.text_features(ids, in_dim)
+
+    vocab = featurize.QueryVocab()
+    flat = featurize.flatten(sess, vocab)
+    titles = {0: 'UNK'}
+    for s in sess:
+        for act in s:
+            if act[1] != sessions.SEARCH:
+                titles.setdefault(act[-1], act[-2] if act[-2] is not None else '')
+    item_ids = sorted(titles)
+    cache = featurize.FeatureCache(feats(sorted(vocab.ids, key=vocab.ids.get)), item_ids,
+                                   feats([titles[i] for i in item_ids]), 0)
+    out_native = enc(featurize.featurize_batch(flat, cache))
+    out_python = enc(graph.collate(graphs).to("cuda"))
+    assert torch.equal(out_native, out_python)
+    # (a sub-batch is its own batch: the GAT self-loop quirk ties embeddings to the batch composition, SURVEY 8a7)
+    part = enc(featurize.featurize_batch(flat.slice(100, 200), cache))
+    assert torch.equal(part, enc(graph.collate(graphs[100:200]).to("cuda")))
+
+
 def test_nan_input_raises_like_the_reference():
     import sessionsimilaritysearch_b200 as sss
     from sessionsimilaritysearch_b200 import graph, sessions

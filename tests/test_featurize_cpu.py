@@ -1,0 +1,95 @@
+"""Native batched featuriser (sss_featurize_batch, host code of libsss_b200.so) against
+(1) the graphs the REFERENCE's own sequence_to_graph built (tests/golden/graphs_golden.npz) and
+(2) the Python mirror + collate on larger seeded batches, array for array."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from sessionsimilaritysearch_b200 import featurize, graph, sessions, synth  # noqa: E402
+
+GG = np.load(os.path.join(HERE, "golden", "graphs_golden.npz"))
+
+
+def _sessions_of_the_goldens():
+    sess = synth.make_sessions(24, 5)
+    sess[3] = [a for a in sess[3] if a[1] == 's'] or sess[3]
+    return sess
+
+
+@pytest.mark.parametrize("ignore_query", [False, True])
+def test_native_featuriser_matches_the_reference_graphs(ignore_query):
+    sess = _sessions_of_the_goldens()
+    if ignore_query:
+        sess = sess[:6]
+    prefix = "ig_g%d" if ignore_query else "g%d"
+    flat = featurize.flatten(sess, featurize.QueryVocab(), ignore_query=ignore_query)
+    a = featurize.featurize_arrays(flat)
+    q0 = p0 = e0 = qp0 = pp0 = 0
+    for i in range(len(sess)):
+        g = prefix % i
+        nq = len(GG[g + "_query_pos_emb_id"])
+        npn = len(GG[g + "_product_x"])
+        ne = len(GG[g + "_product_pos_emb_id"])
+        assert np.array_equal(a["query_pos"][q0:q0 + nq], GG[g + "_query_pos_emb_id"])
+        assert np.all(a["query_batch"][q0:q0 + nq] == i)
+        assert np.array_equal(a["product_key"][p0:p0 + npn], GG[g + "_product_x"])
+        assert np.array_equal(a["product_cnt"][p0:p0 + npn], GG[g + "_product_cnt"])
+        assert np.array_equal(a["last_click_mask"][p0:p0 + npn], GG[g + "_product_last_click_mask"])
+        assert np.array_equal(a["product_pos"][e0:e0 + ne], GG[g + "_product_pos_emb_id"])
+        qp = GG[g + "_qp"]
+        n_qp = qp.shape[1]
+        assert np.array_equal(a["qp_src"][qp0:qp0 + n_qp] - q0, qp[0])
+        assert np.array_equal(a["qp_dst"][qp0:qp0 + n_qp] - p0, qp[1])
+        pp = GG[g + "_pp"]
+        n_pp = pp.shape[1]
+        assert np.array_equal(a["pp_src"][pp0:pp0 + n_pp] - p0, pp[0])
+        assert np.array_equal(a["pp_dst"][pp0:pp0 + n_pp] - p0, pp[1])
+        assert np.array_equal(a["pp_weight"][pp0:pp0 + n_pp], GG[g + "_pp_w"])
+        q0, p0, e0, qp0, pp0 = q0 + nq, p0 + npn, e0 + ne, qp0 + n_qp, pp0 + n_pp
+    assert (q0, p0, e0, qp0, pp0) == (len(a["query_pos"]), len(a["product_key"]), len(a["product_pos"]),
+                                      len(a["qp_src"]), len(a["pp_src"]))
+
+
+@pytest.mark.parametrize("n,threads", [(1, 1), (700, 1), (6000, 4)])
+def test_native_featuriser_equals_python_mirror_plus_collate(n, threads):
+    tok = synth.HashTokenizer()
+    sess = synth.make_sessions(n, 100 + n)
+    if n > 3:
+        sess[2] = [a for a in sess[2] if a[1] == 's'] or sess[2]          # item-less
+        sess[3] = [a for a in sess[3] if a[1] != 's'] or sess[3]          # search-less
+    vocab = featurize.QueryVocab()
+    a = featurize.featurize_arrays(featurize.flatten(sess, vocab), n_threads=threads)
+    b = graph.collate([sessions.sequence_to_graph(0, s, s[:1], tok, 20) for s in sess])
+    ei = b.edge_index_dict
+    want = {"query_pos": b["query"].pos_emb_id, "query_batch": b["query"].batch, "product_key": b["product"].x,
+            "product_cnt": b["product"].cnt, "product_pos": b["product"].pos_emb_id,
+            "product_batch": b["product"].batch, "last_click_mask": b["product"].last_click_mask,
+            "qp_src": ei[graph.EDGE_QP][0], "qp_dst": ei[graph.EDGE_QP][1], "pp_src": ei[graph.EDGE_PP][0],
+            "pp_dst": ei[graph.EDGE_PP][1], "pp_weight": b[graph.EDGE_PP].edge_weight}
+    for k, v in want.items():
+        assert np.array_equal(a[k], v.numpy()), k
+    assert np.array_equal(np.stack([a["qp_dst"], a["qp_src"]]), ei[graph.EDGE_PQ].numpy())
+    # the text key of a query node is the vocabulary id of its string; node 0 of every session is the empty string
+    words = [w for s in sess
+             for w in [""] + [(act[2] if act[2] is not None else "") for act in s if act[1] == sessions.SEARCH]]
+    assert [vocab(w) for w in words] == a["query_key"].tolist()
+
+
+def test_native_featuriser_rejects_inconsistent_input():
+    flat = featurize.flatten(synth.make_sessions(5, 1), featurize.QueryVocab())
+    flat.uniq_items[0] += 12345  # an item event whose id is not in the session's distinct list
+    with pytest.raises(RuntimeError, match="distinct-item list"):
+        featurize.featurize_arrays(flat)
+
+
+def test_flat_sessions_slice():
+    sess = synth.make_sessions(50, 9)
+    flat = featurize.flatten(sess, featurize.QueryVocab())
+    part = featurize.featurize_arrays(flat.slice(10, 30))
+    whole = featurize.featurize_arrays(featurize.flatten(sess[10:30], featurize.QueryVocab()))
+    for k in ("query_pos", "product_key", "product_pos", "qp_src", "pp_dst"):
+        assert np.array_equal(part[k], whole[k])
