@@ -462,7 +462,8 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     RF_PHASE(4);  // survivors + reset
     // ---- D. exact fixed-order re-scoring of the survivors: one lane walks one row in k-ascending order with a
     // single accumulator (the oracle's rounding sequence).  A lane streams its own row as 16-byte loads, 64 bytes
-    // (two sectors) per step with the next step already in flight; the second half of every sector is an L1 hit.
+    // (two sectors) per step with the next step already in flight; the second half of every sector is an L1 hit
+    // (bypassing L1 with ld.global.cg was measured 1.5x slower on 1600-wide rows: profiles/r01_ab_experiments.md).
     if ((a.d & 3) == 0) {
       const int d4 = a.d >> 2;
       const float4* qs4 = reinterpret_cast<const float4*>(sm.qs);
