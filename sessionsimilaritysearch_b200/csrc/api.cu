@@ -468,9 +468,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       SSS_CUDA_OK(cudaMemsetAsync(ix->dbg, 0, 12 * sizeof(unsigned long long), st));
       ra.debug = ix->dbg;
     }
-    // Bootstrap: one tensor-core pass in chunk-max mode over the first 128K rows gives every query a valid
-    // threshold at once and replaces the first five doubling waves (and, in EXACT mode, the fp32 first wave).
-    const int64_t kBootRows = 131072;
+    // Bootstrap: one tensor-core pass in chunk-max mode over the first rows (128K; for smaller indexes the largest
+    // power of two within half of the rows) gives every query a valid threshold at once and replaces the short first
+    // waves (and, in EXACT mode, the fp32 first wave and the per-wave re-scoring: lazy mode needs tensor waves only).
+    int64_t kBootRows = 131072;
+    while (kBootRows > 4096 && kBootRows * 2 > n_rows) kBootRows >>= 1;
     const int n_boot_chunks = (int)(kBootRows / 32);
     const bool grouped = ix->reduce == SSS_REDUCE_MAX;
     const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
