@@ -190,6 +190,7 @@ def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
                              device=device)
     _, graphs = ec.make_graphs(n_sessions, in_dim, 17, sessions.sequence_to_graph)
     batches = [graph.collate(graphs[i:i + batch]).to("cuda:%d" % device) for i in range(0, n_sessions, batch)]
+    enc.set_math("fp32")  # first figure: cuBLAS pedantic sgemm (the bit-faithful arithmetic)
     for b in batches[:2]:
         enc(b)
     torch.cuda.synchronize()
@@ -201,6 +202,18 @@ def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
     torch.cuda.synchronize()
     out = {"encoder_sessions_per_s": n_sessions / (e0.elapsed_time(e1) * 1e-3),
            "encoder_nodes_per_batch": int(batches[0]['query'].x.shape[0] + batches[0]['product'].x.shape[0])}
+    try:  # dense linears on this library's split-bf16 tcgen05 GEMM
+        enc.set_math("bf16x3")
+        for b in batches[:2]:
+            enc(b)
+        e0.record()
+        for b in batches:
+            enc(b)
+        e1.record()
+        torch.cuda.synchronize()
+        out["encoder_bf16x3_sessions_per_s"] = n_sessions / (e0.elapsed_time(e1) * 1e-3)
+    except RuntimeError as e:
+        out["encoder_bf16x3_sessions_per_s"] = "error: %s" % str(e)[:120]
     try:  # dense linears on the bf16 tensor cores (cuBLAS fp32 emulation), when the loaded cuBLAS has it
         enc.set_math("bf16x9")
         for b in batches[:2]:

@@ -182,8 +182,11 @@ int sss_encoder_forward(sss_encoder_t* enc, const sss_graph_batch_t* batch, floa
 /* Arithmetic of the encoder's dense linears.  SSS_ENCODER_MATH_FP32 (default): cuBLAS sgemm, pedantic fp32 on the
  * CUDA cores.  SSS_ENCODER_MATH_BF16X9: cuBLAS' fp32 emulation on the bf16 tensor cores (each operand split into
  * three bf16 terms, nine products, fp32-level accuracy; cuBLAS >= 12.9 on sm_100) — returns non-zero and leaves the
- * mode unchanged when the loaded cuBLAS does not offer it.  sss_encoder_get_math returns the active mode. */
-enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1 };
+ * mode unchanged when the loaded cuBLAS does not offer it.  SSS_ENCODER_MATH_BF16X3: this library's own tcgen05 GEMM
+ * (csrc/gemm_bf16x3_sm100.cu): operands split into hi + lo bf16, three products accumulated in fp32 in TMEM; through
+ * the whole encoder 2.7e-5 of the output scale from a float64 forward (pedantic fp32: 2.5e-6).
+ * sss_encoder_get_math returns the active mode. */
+enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1, SSS_ENCODER_MATH_BF16X3 = 2 };
 int sss_encoder_set_math(sss_encoder_t* enc, int math);
 int sss_encoder_get_math(const sss_encoder_t* enc);
 

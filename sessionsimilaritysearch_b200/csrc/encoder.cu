@@ -19,6 +19,7 @@
 
 #include "../../include/sss_b200.h"
 #include "common.cuh"
+#include "kernels.h"
 
 namespace sss {
 
@@ -333,6 +334,15 @@ struct sss_encoder {
   std::map<std::string, int64_t> numel;
   cublasHandle_t blas = nullptr;
   int math = SSS_ENCODER_MATH_FP32;
+  // split-bf16 copies for the tensor-core GEMM (SSS_ENCODER_MATH_BF16X3): weights once per (pointer, shape),
+  // activations once per forward (several linears read the same node features)
+  struct Split {
+    const float* src; int rows, cols; int64_t ld; int transposed;
+    void* hi; void* lo; int rows_pad, cols_pad;
+  };
+  std::vector<Split> w_split;   // persistent (cudaMalloc), dropped when a parameter is replaced
+  std::vector<Split> a_split;   // arena, per forward
+  int* gemm_flag = nullptr;     // watchdog code of the tensor-core GEMM
   // Workspace arena: slabs are bump-allocated per forward call and kept across calls (cudaMalloc/cudaFree per
   // buffer cost more than the whole forward).  A call that needed more than one slab is followed by one
   // consolidation at the start of the next call; `done` orders reuse across streams.
@@ -360,6 +370,7 @@ int ws_begin(sss_encoder* e, cudaStream_t st) {
   if (e->done_recorded) SSS_CUDA_OK(cudaStreamWaitEvent(st, e->done, 0));
   e->used = 0;
   e->requested = 0;
+  e->a_split.clear();
   return 0;
 }
 int ws_end(sss_encoder* e, cudaStream_t st) {
@@ -390,6 +401,52 @@ void ws_release(sss_encoder* e) {
   e->done = nullptr;
   e->done_recorded = false;
 }
+void drop_weight_splits(sss_encoder* e) {
+  for (auto& s : e->w_split) {
+    cudaFree(s.hi);
+    cudaFree(s.lo);
+  }
+  e->w_split.clear();
+}
+
+// C[M,N] (ldc) = A[M,K] (lda) * op(B): b_transposed == 0: B is [N,K] row-major (ldb) -> x @ W.T;
+//                                      b_transposed == 1: B is [K,N] row-major (ldb) -> x @ W
+int enc_gemm(sss_encoder* e, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             int b_transposed, float* C, int ldc) {
+  if (M == 0 || N == 0) return 0;
+  if (e->math != SSS_ENCODER_MATH_BF16X3)
+    return b_transposed ? gemm_nn(e->blas, M, N, K, A, lda, B, ldb, C, ldc) : gemm_nt(e->blas, M, N, K, A, lda, B, ldb, C, ldc);
+  const int k_pad = (K + 63) / 64 * 64;
+  auto find = [](std::vector<sss_encoder::Split>& v, const float* src, int rows, int cols, int64_t ld, int tr) {
+    for (auto& s : v)
+      if (s.src == src && s.rows == rows && s.cols == cols && s.ld == ld && s.transposed == tr) return &s;
+    return (sss_encoder::Split*)nullptr;
+  };
+  sss_encoder::Split* ws = find(e->w_split, B, N, K, ldb, b_transposed);
+  if (!ws) {
+    sss_encoder::Split s{B, N, K, (int64_t)ldb, b_transposed, nullptr, nullptr, (N + 127) / 128 * 128, k_pad};
+    const size_t bytes = (size_t)s.rows_pad * s.cols_pad * 2;
+    SSS_CUDA_OK(cudaMalloc(&s.hi, bytes));
+    SSS_CUDA_OK(cudaMalloc(&s.lo, bytes));
+    if (launch_split_bf16(B, N, K, ldb, b_transposed, s.hi, s.lo, s.rows_pad, s.cols_pad, st)) return 1;
+    e->w_split.push_back(s);
+    ws = &e->w_split.back();
+  }
+  sss_encoder::Split* as = find(e->a_split, A, M, K, lda, 0);
+  if (!as) {
+    sss_encoder::Split s{A, M, K, (int64_t)lda, 0, nullptr, nullptr, (M + 127) / 128 * 128, k_pad};
+    uint16_t *hi, *lo;
+    if (ws_alloc(e, &hi, (size_t)s.rows_pad * s.cols_pad) || ws_alloc(e, &lo, (size_t)s.rows_pad * s.cols_pad)) return 1;
+    s.hi = hi;
+    s.lo = lo;
+    if (launch_split_bf16(A, M, K, lda, 0, s.hi, s.lo, s.rows_pad, s.cols_pad, st)) return 1;
+    e->a_split.push_back(s);
+    as = &e->a_split.back();
+  }
+  return launch_gemm_bf16x3(as->hi, as->lo, as->rows_pad, ws->hi, ws->lo, ws->rows_pad, k_pad, C, M, N, ldc,
+                            e->gemm_flag, st);
+}
+
 struct Csr {
   int* rowptr = nullptr;
   int* col = nullptr;
@@ -455,7 +512,8 @@ extern "C" int sss_encoder_create(sss_encoder_t** out, int device, const sss_enc
 
 extern "C" int sss_encoder_set_math(sss_encoder_t* e, int math) {
   SSS_REQUIRE(e != nullptr, "sss_encoder_set_math: NULL encoder");
-  SSS_REQUIRE(math == SSS_ENCODER_MATH_FP32 || math == SSS_ENCODER_MATH_BF16X9, "sss_encoder_set_math: unknown mode");
+  SSS_REQUIRE(math == SSS_ENCODER_MATH_FP32 || math == SSS_ENCODER_MATH_BF16X9 || math == SSS_ENCODER_MATH_BF16X3,
+              "sss_encoder_set_math: unknown mode");
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(e->device);
@@ -466,6 +524,10 @@ extern "C" int sss_encoder_set_math(sss_encoder_t* e, int math) {
     if (rc != 0) g_cublas.set_math(e->blas, kPedanticMath);
   } else {
     rc = g_cublas.set_math(e->blas, kPedanticMath);
+    if (rc == 0 && math == SSS_ENCODER_MATH_BF16X3 && !e->gemm_flag) {
+      rc = cudaMalloc((void**)&e->gemm_flag, sizeof(int)) == cudaSuccess ? 0 : 1;
+      if (rc == 0) rc = cudaMemset(e->gemm_flag, 0, sizeof(int)) == cudaSuccess ? 0 : 1;
+    }
   }
   cudaSetDevice(prev);
   SSS_REQUIRE(rc == 0, "the loaded cuBLAS does not offer fp32 emulation on bf16 tensor cores (BF16x9 needs cuBLAS >= 12.9)");
@@ -481,6 +543,8 @@ extern "C" int sss_encoder_destroy(sss_encoder_t* e) {
   cudaGetDevice(&prev);
   cudaSetDevice(e->device);
   for (auto& kv : e->params) cudaFree(kv.second);
+  drop_weight_splits(e);
+  if (e->gemm_flag) cudaFree(e->gemm_flag);
   ws_release(e);
   if (e->blas) g_cublas.destroy(e->blas);
   cudaSetDevice(prev);
@@ -495,6 +559,7 @@ extern "C" int sss_encoder_set_param(sss_encoder_t* e, const char* name, const f
   cudaGetDevice(&prev);
   cudaSetDevice(e->device);
   std::string k(name);
+  drop_weight_splits(e);  // split-bf16 copies are keyed by pointer: a replaced parameter may reuse an address
   auto it = e->params.find(k);
   if (it != e->params.end()) {
     cudaFree(it->second);
@@ -569,6 +634,7 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
   // ---- HeteroGGNN layers
   for (int l = 0; l < L; ++l) {
     const int cin = l == 0 ? IN : H;
+    e->a_split.clear();  // activation splits are keyed by pointer and buffers such as Agg are rewritten every layer
     const int off = l == 0 ? 0 : IN + (l - 1) * H;
     const int off_next = IN + l * H;
     const std::string pre = "gnn.convs." + std::to_string(l) + ".convs.";
@@ -587,12 +653,12 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
     const float* Xq = Zq + off;
     const float* Xp = Zp + off;
     // query side: S_qp (source of q->p) | T_pq (destination of p->q)
-    if (gemm_nt(e->blas, NQ, H, cin, Xq, ZD, w_qp_src, cin, Sq, 2 * H)) return 1;
-    if (gemm_nt(e->blas, NQ, H, cin, Xq, ZD, w_pq_dst, cin, Sq + H, 2 * H)) return 1;
+    if (enc_gemm(e, st, NQ, H, cin, Xq, ZD, w_qp_src, cin, 0, Sq, 2 * H)) return 1;
+    if (enc_gemm(e, st, NQ, H, cin, Xq, ZD, w_pq_dst, cin, 0, Sq + H, 2 * H)) return 1;
     // product side: T_qp | S_pq | M = pad(x) @ W_g
-    if (gemm_nt(e->blas, NP, H, cin, Xp, ZD, w_qp_dst, cin, Sp, 3 * H)) return 1;
-    if (gemm_nt(e->blas, NP, H, cin, Xp, ZD, w_pq_src, cin, Sp + H, 3 * H)) return 1;
-    if (gemm_nn(e->blas, NP, H, cin, Xp, ZD, w_g, H, Sp + 2 * H, 3 * H)) return 1;
+    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_qp_dst, cin, 0, Sp, 3 * H)) return 1;
+    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_pq_src, cin, 0, Sp + H, 3 * H)) return 1;
+    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_g, H, 1, Sp + 2 * H, 3 * H)) return 1;
     rowdot_kernel<<<(NQ + 7) / 8, 256, 0, st>>>(Sq, 2 * H, NQ, H, a_qp_src, as_q);        // a_s of q->p
     rowdot_kernel<<<(NQ + 7) / 8, 256, 0, st>>>(Sq + H, 2 * H, NQ, H, a_pq_dst, ad_q);    // a_d of p->q
     rowdot_kernel<<<(NP + 7) / 8, 256, 0, st>>>(Sp, 3 * H, NP, H, a_qp_dst, ad_p);        // a_d of q->p
@@ -603,21 +669,22 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
     gat_aggregate_kernel<<<NQ, 256, 0, st>>>(pq.rowptr, pq.col, Sp + H, 3 * H, as_p, ad_q, b_pq, H, Zq + off_next, ZD, 1);
     // GatedGraphConv: aggregate, GRU
     segsum_rows_kernel<<<NP, 256, 0, st>>>(pp.rowptr, pp.col, Sp + 2 * H, 3 * H, H, Agg, H);
-    if (gemm_nt(e->blas, NP, 3 * H, H, Agg, H, w_ih, H, gi, 3 * H)) return 1;
-    if (gemm_nt(e->blas, NP, 3 * H, cin, Xp, ZD, w_hh, H, gh, 3 * H)) return 1;  // pad(x) @ W_hh^T = x @ W_hh[:, :cin]^T
+    if (enc_gemm(e, st, NP, 3 * H, H, Agg, H, w_ih, H, 0, gi, 3 * H)) return 1;
+    if (enc_gemm(e, st, NP, 3 * H, cin, Xp, ZD, w_hh, H, 0, gh, 3 * H)) return 1;  // pad(x) @ W_hh^T = x @ W_hh[:, :cin]^T
     gru_relu_kernel<<<(unsigned)(((int64_t)NP * H + 255) / 256), 256, 0, st>>>(gi, gh, b_ih, b_hh, Xp, ZD, cin, Gp, NP, H,
                                                                                Zp + off_next, ZD);
   }
 
   // ---- PositionalAttentionPooling
+  e->a_split.clear();
   const float *wq = P(e, "pooling.query_lin.weight", (int64_t)LIN * ZD), *bq = P(e, "pooling.query_lin.bias", LIN),
               *wp = P(e, "pooling.product_lin.weight", (int64_t)LIN * ZD), *bp = P(e, "pooling.product_lin.bias", LIN),
               *pe = P(e, "pooling.positional_emb.weight", (int64_t)MSL * MSL),
               *wn = P(e, "pooling.node_emb_lin.weight", (int64_t)OUT * OUT), *bn = P(e, "pooling.node_emb_lin.bias", OUT),
               *wc = P(e, "pooling.coarse_rep_lin.weight", (int64_t)OUT * OUT), *wa = P(e, "pooling.att_lin.weight", OUT);
   if (!wq || !bq || !wp || !bp || !pe || !wn || !bn || !wc || !wa) return 1;
-  if (gemm_nt(e->blas, NQ, LIN, ZD, Zq, ZD, wq, ZD, uq_lin, LIN)) return 1;
-  if (gemm_nt(e->blas, NP, LIN, ZD, Zp, ZD, wp, ZD, up_lin, LIN)) return 1;
+  if (enc_gemm(e, st, NQ, LIN, ZD, Zq, ZD, wq, ZD, 0, uq_lin, LIN)) return 1;
+  if (enc_gemm(e, st, NP, LIN, ZD, Zp, ZD, wp, ZD, 0, up_lin, LIN)) return 1;
   cnt_to_int_kernel<<<(NP + 255) / 256, 256, 0, st>>>(bt->product_cnt, NP, cnt_i);
   csr_scan_kernel<<<1, 1024, 0, st>>>(cnt_i, NP, cnt_pre, cursor_tmp);
   expand_map_kernel<<<(NP + 127) / 128, 128, 0, st>>>(cnt_pre, NP, occ_prod);
@@ -626,8 +693,8 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
   SSS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int) * (size_t)B * 4, st));
   graph_ranges_kernel<<<(NT + 255) / 256, 256, 0, st>>>(node_graph, NE, NT, ranges);
   graph_mean_kernel<<<B, 256, 0, st>>>(U, OUT, ranges, nullptr, coarse);
-  if (gemm_nt(e->blas, NT, OUT, OUT, U, OUT, wn, OUT, Aatt, OUT)) return 1;
-  if (gemm_nt(e->blas, B, OUT, OUT, coarse, OUT, wc, OUT, Bc, OUT)) return 1;
+  if (enc_gemm(e, st, NT, OUT, OUT, U, OUT, wn, OUT, 0, Aatt, OUT)) return 1;
+  if (enc_gemm(e, st, B, OUT, OUT, coarse, OUT, wc, OUT, 0, Bc, OUT)) return 1;
   pool_att_kernel<<<NT, 256, 0, st>>>(Aatt, bn, Bc, node_graph, wa, OUT, att);
   graph_mean_kernel<<<B, 256, 0, st>>>(U, OUT, ranges, att, out);
   SSS_CUDA_OK(cudaGetLastError());

@@ -47,6 +47,11 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream);
 unsigned long long* scan_prof_buffer();  // experiments only (SSS_SCAN_PROF)
+// gemm_bf16x3_sm100.cu — split-bf16 tensor-core GEMM of the encoder: C[M,N] = A[M,K] * B[N,K]^T
+int launch_split_bf16(const float* x, int rows, int cols, int64_t ld, int transposed, void* hi, void* lo, int rows_pad,
+                      int cols_pad, cudaStream_t stream);
+int launch_gemm_bf16x3(const void* a_hi, const void* a_lo, int m_pad, const void* b_hi, const void* b_lo, int n_pad,
+                       int k_pad, float* C, int M, int N, int ldc, int* err_flag, cudaStream_t stream);
 // select.cu — bootstrap thresholds from chunk maxima: thr[q] = just below (2k-th largest chunk max - slack)
 int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
                          float slack_mult, SelectState st, cudaStream_t stream);

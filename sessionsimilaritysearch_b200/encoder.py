@@ -28,7 +28,8 @@ def _f32(t, dev):
 
 
 class SessionEncoder:
-    def __init__(self, params, in_dim=768, hidden=800, n_layers=3, out_dim=1600, max_seq_len=20, device=None):
+    def __init__(self, params, in_dim=768, hidden=800, n_layers=3, out_dim=1600, max_seq_len=20, device=None,
+                 math="bf16x3"):
         self._lib = _lib.load()
         self.device = _lib.current_device() if device is None else int(device)
         self.in_dim, self.hidden, self.n_layers, self.out_dim, self.max_seq_len = in_dim, hidden, n_layers, out_dim, max_seq_len
@@ -37,6 +38,9 @@ class SessionEncoder:
         check(self._lib.sss_encoder_create(ctypes.byref(h), self.device, ctypes.byref(shape)))
         self._h = h
         self.load_state_dict(params)
+        # dense linears: this library's split-bf16 tcgen05 GEMM by default (2.7e-5 of the output scale from float64);
+        # math="fp32" selects cuBLAS' pedantic sgemm (2.5e-6), the C ABI's own default
+        self.set_math(math)
 
     @classmethod
     def from_module(cls, module, **kw):
@@ -60,14 +64,15 @@ class SessionEncoder:
         return n
 
     def set_math(self, math):
-        """'fp32' (cuBLAS pedantic sgemm, default) or 'bf16x9' (cuBLAS fp32 emulation on the bf16 tensor cores);
-        raises RuntimeError when the loaded cuBLAS does not offer the emulation"""
-        check(self._lib.sss_encoder_set_math(self._h, {"fp32": 0, "bf16x9": 1}[math]))
+        """'fp32' (cuBLAS pedantic sgemm, default), 'bf16x3' (this library's tcgen05 GEMM on split-bf16 operands:
+        fp32-level accuracy on the tensor cores) or 'bf16x9' (cuBLAS' fp32 emulation; raises RuntimeError when the
+        loaded cuBLAS does not offer it)"""
+        check(self._lib.sss_encoder_set_math(self._h, {"fp32": 0, "bf16x9": 1, "bf16x3": 2}[math]))
         return self
 
     @property
     def math(self):
-        return ("fp32", "bf16x9")[int(self._lib.sss_encoder_get_math(self._h))]
+        return ("fp32", "bf16x9", "bf16x3")[int(self._lib.sss_encoder_get_math(self._h))]
 
     def eval(self):
         return self

@@ -68,7 +68,7 @@ def test_encoder_bf16x9_tensor_core_linears_match_fp32():
     P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 5)
     enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
     data = graph.collate(graphs).to("cuda")
-    assert enc.math == "fp32"
+    enc.set_math("fp32")
     out32 = enc(data).cpu().numpy()
     try:
         enc.set_math("bf16x9")
@@ -116,6 +116,34 @@ def test_native_featuriser_feeds_the_encoder_like_the_python_path():
     # (a sub-batch is its own batch: the GAT self-loop quirk ties embeddings to the batch composition)
     part = enc(featurize.featurize_batch(flat.slice(100, 200), cache))
     assert torch.equal(part, enc(graph.collate(graphs[100:200]).to("cuda")))
+
+
+@pytest.mark.parametrize("shape", [(768, 800, 3, 1600, 40), (48, 64, 3, 100, 200)])
+def test_encoder_bf16x3_tcgen05_linears_match_fp32(shape):
+    """dense linears on this library's split-bf16 tcgen05 GEMM (sss_encoder_set_math BF16X3): inside the same tolerance
+    against the oracle as the pedantic fp32 path, deterministic, and switchable back"""
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from sessionsimilaritysearch_b200 import graph, sessions
+    in_dim, hidden, n_layers, out_dim, n_sess = shape
+    msl = 20
+    _, graphs = ec.make_graphs(n_sess, in_dim, 5, sessions.sequence_to_graph)
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 5)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    data = graph.collate(graphs).to("cuda")
+    assert enc.math == "bf16x3"      # the Python facade's default
+    enc.set_math("fp32")
+    out32 = enc(data).cpu().numpy()
+    enc.set_math("bf16x3")
+    assert enc.math == "bf16x3"
+    out3 = enc(data).cpu().numpy()
+    ref = eo.encoder_forward(P, eo.batch_from_pyg(graph.collate(graphs)), n_layers).numpy()
+    scale = float(np.abs(ref).max())
+    np.testing.assert_allclose(out3, ref, rtol=3e-4, atol=3e-4 * scale)
+    assert float(np.abs(out3 - out32).max()) <= 1e-4 * scale
+    assert np.array_equal(enc(data).cpu().numpy(), out3)
+    enc.set_math("fp32")
+    assert np.array_equal(enc(data).cpu().numpy(), out32)
 
 
 def test_nan_input_raises_like_the_reference():
