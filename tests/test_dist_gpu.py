@@ -23,7 +23,7 @@ def test_sharded_search_matches_single_gpu(world):
     if _n_gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-           "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "scripts", "dist_check.py")]
+           "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "tools", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_CHECK_OK" in r.stdout
