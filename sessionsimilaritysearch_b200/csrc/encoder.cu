@@ -447,6 +447,64 @@ int enc_gemm(sss_encoder* e, cudaStream_t st, int M, int N, int K, const float* 
                             e->gemm_flag, st);
 }
 
+// Several linears that read the same input, written side by side into C (column blocks of widths n[i]):
+//   C[:, off_i : off_i + n_i] = A * op(B_i).  On the tensor-core path they run as ONE GEMM against the row-wise
+// concatenation of the (split) weights; otherwise one library GEMM each.
+struct LinPart {
+  const float* B;
+  int ldb, transposed, n;
+};
+int enc_gemm_fused(sss_encoder* e, cudaStream_t st, int M, int K, const float* A, int lda, const LinPart* parts,
+                   int n_parts, float* C, int ldc) {
+  int n_total = 0;
+  for (int i = 0; i < n_parts; ++i) n_total += parts[i].n;
+  if (e->math != SSS_ENCODER_MATH_BF16X3 || n_parts == 1) {
+    int off = 0;
+    for (int i = 0; i < n_parts; ++i) {
+      if (enc_gemm(e, st, M, parts[i].n, K, A, lda, parts[i].B, parts[i].ldb, parts[i].transposed, C + off, ldc)) return 1;
+      off += parts[i].n;
+    }
+    return 0;
+  }
+  if (M == 0 || n_total == 0) return 0;
+  const int k_pad = (K + 63) / 64 * 64;
+  // the fused weight is cached under the first part's pointer with the total row count (rows = n_total marks it)
+  sss_encoder::Split* ws = nullptr;
+  for (auto& s : e->w_split)
+    if (s.src == parts[0].B && s.rows == n_total && s.cols == K && s.ld == -(int64_t)n_parts) ws = &s;
+  if (!ws) {
+    sss_encoder::Split s{parts[0].B, n_total, K, -(int64_t)n_parts, 0, nullptr, nullptr, (n_total + 127) / 128 * 128, k_pad};
+    const size_t bytes = (size_t)s.rows_pad * s.cols_pad * 2;
+    SSS_CUDA_OK(cudaMalloc(&s.hi, bytes));
+    SSS_CUDA_OK(cudaMalloc(&s.lo, bytes));
+    int off = 0;
+    for (int i = 0; i < n_parts; ++i) {
+      const int rows_out = i + 1 == n_parts ? s.rows_pad - off : parts[i].n;  // the last part also zeroes the padding
+      if (launch_split_bf16(parts[i].B, parts[i].n, K, parts[i].ldb, parts[i].transposed,
+                            (uint16_t*)s.hi + (size_t)off * k_pad, (uint16_t*)s.lo + (size_t)off * k_pad, rows_out, k_pad, st))
+        return 1;
+      off += parts[i].n;
+    }
+    e->w_split.push_back(s);
+    ws = &e->w_split.back();
+  }
+  sss_encoder::Split* as = nullptr;
+  for (auto& s : e->a_split)
+    if (s.src == A && s.rows == M && s.cols == K && s.ld == lda) as = &s;
+  if (!as) {
+    sss_encoder::Split s{A, M, K, (int64_t)lda, 0, nullptr, nullptr, (M + 127) / 128 * 128, k_pad};
+    uint16_t *hi, *lo;
+    if (ws_alloc(e, &hi, (size_t)s.rows_pad * s.cols_pad) || ws_alloc(e, &lo, (size_t)s.rows_pad * s.cols_pad)) return 1;
+    s.hi = hi;
+    s.lo = lo;
+    if (launch_split_bf16(A, M, K, lda, 0, s.hi, s.lo, s.rows_pad, s.cols_pad, st)) return 1;
+    e->a_split.push_back(s);
+    as = &e->a_split.back();
+  }
+  return launch_gemm_bf16x3(as->hi, as->lo, as->rows_pad, ws->hi, ws->lo, ws->rows_pad, k_pad, C, M, n_total, ldc,
+                            e->gemm_flag, st);
+}
+
 struct Csr {
   int* rowptr = nullptr;
   int* col = nullptr;
@@ -653,12 +711,11 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
     const float* Xq = Zq + off;
     const float* Xp = Zp + off;
     // query side: S_qp (source of q->p) | T_pq (destination of p->q)
-    if (enc_gemm(e, st, NQ, H, cin, Xq, ZD, w_qp_src, cin, 0, Sq, 2 * H)) return 1;
-    if (enc_gemm(e, st, NQ, H, cin, Xq, ZD, w_pq_dst, cin, 0, Sq + H, 2 * H)) return 1;
+    const LinPart q_parts[2] = {{w_qp_src, cin, 0, H}, {w_pq_dst, cin, 0, H}};
+    if (enc_gemm_fused(e, st, NQ, cin, Xq, ZD, q_parts, 2, Sq, 2 * H)) return 1;
     // product side: T_qp | S_pq | M = pad(x) @ W_g
-    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_qp_dst, cin, 0, Sp, 3 * H)) return 1;
-    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_pq_src, cin, 0, Sp + H, 3 * H)) return 1;
-    if (enc_gemm(e, st, NP, H, cin, Xp, ZD, w_g, H, 1, Sp + 2 * H, 3 * H)) return 1;
+    const LinPart p_parts[3] = {{w_qp_dst, cin, 0, H}, {w_pq_src, cin, 0, H}, {w_g, H, 1, H}};
+    if (enc_gemm_fused(e, st, NP, cin, Xp, ZD, p_parts, 3, Sp, 3 * H)) return 1;
     rowdot_kernel<<<(NQ + 7) / 8, 256, 0, st>>>(Sq, 2 * H, NQ, H, a_qp_src, as_q);        // a_s of q->p
     rowdot_kernel<<<(NQ + 7) / 8, 256, 0, st>>>(Sq + H, 2 * H, NQ, H, a_pq_dst, ad_q);    // a_d of p->q
     rowdot_kernel<<<(NP + 7) / 8, 256, 0, st>>>(Sp, 3 * H, NP, H, a_qp_dst, ad_p);        // a_d of q->p

@@ -180,8 +180,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int col
 
 int launch_split_bf16(const float* x, int rows, int cols, int64_t ld, int transposed, void* hi, void* lo, int rows_pad,
                       int cols_pad, cudaStream_t stream) {
-  SSS_REQUIRE(rows_pad % 128 == 0 && cols_pad % 64 == 0 && rows_pad >= rows && cols_pad >= cols,
-              "split_bf16: bad padded shape");
+  // (rows_pad is the number of rows WRITTEN, zero beyond `rows`: a whole operand, or one part of a fused weight)
+  SSS_REQUIRE(cols_pad % 64 == 0 && rows_pad >= rows && cols_pad >= cols, "split_bf16: bad padded shape");
   const int64_t total = (int64_t)rows_pad * cols_pad;
   if (total == 0) return 0;
   int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
