@@ -16,20 +16,27 @@
 namespace sss {
 
 // ---- refine ------------------------------------------------------------------------------------------
-// Per query and wave.  Input: the retained entries [0, nret) of the query's list (final keys, ids as returned)
-// plus the NEW row-level candidates of the last scan wave, which arrive either
+// Per query and wave.  Input: the retained entries [0, nret) of the query's list plus the NEW row-level candidates of
+// the last scan wave, which arrive either
 //   * as list entries [nret, cnt) appended with atomics by the fp32 / Hamming scans, or
 //   * as tensor-core hit records in the query's private sub-regions (a.rec != nullptr): each record holds 32
 //     raw scores, re-filtered here against the threshold the scan used.
-// Steps (all in shared memory, candidates are streamed, never materialised):
-//   1. pass 1 groups candidates by session in a hash table (owner = session, best = max key);
-//   2. EXACT mode only: pass 2 keeps a new row only if its tensor-core score is within 2*margin of its session's
-//      best (|exact - bf16| <= margin, so the others cannot hold the session's exact maximum); the survivors are
-//      re-scored: rows are fetched with coalesced 16-byte loads into a warp-private tile, then lane l walks ITS
-//      row in k-ascending order with one accumulator — the rounding sequence of the fp32 scan and the oracle;
-//   3. per-session max of the final keys, compaction, bitonic sort, keep the best k, raise the threshold.
-// A small instantiation (one block per query, ~35 KB, 6 blocks per SM) serves the common case; queries it cannot
-// hold go on a skip list that a large instantiation (persistent, one block per SM) drains right after.
+// Phases (all in shared memory):
+//   A  compaction: sub-region counters (one load per thread) -> prefix; ONE THREAD PER RECORD loads its 144 bytes,
+//      builds the pass mask and appends the passing rows with one shared-memory atomic per warp;
+//   B  group by session in a hash table (owner = session, best = max key);
+//   S  lazy representation only (EXACT mode, bootstrapped searches, k <= 256): the retained entries are ROWS with
+//      tensor-core keys; a 3-pass radix select gives a lower bound of b_k (k-th best session) and the floor
+//      b_k - 2 * margin below which a session can never decide the result;
+//   C  survivors: rows of live sessions within 2 * margin of their session's best tensor-core score
+//      (|exact - tensor| <= margin, so the others cannot hold the session's exact maximum);
+//   W  lazy, not the last wave: write the survivors back as rows, thr = b_k - 2 * margin — done;
+//   D  otherwise: exact fixed-order re-scoring of the survivors — one lane walks one fp32 row in k-ascending order
+//      with a single accumulator, the rounding sequence of the fp32 scan and the oracle;
+//   E  per-session max of the final keys, gather, sort, keep the best k (eager representation: one exact entry per
+//      session), thr = k-th exact score - margin.
+// A small instantiation (one block per query, 256 threads, ~38 KB, 4 blocks per SM) serves the common case; queries it
+// cannot hold go on a skip list that a large instantiation (persistent, one block per SM) drains right after.
 __device__ __forceinline__ void bitonic_desc(uint64_t* e, int P) {
   for (int k2 = 2; k2 <= P; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
