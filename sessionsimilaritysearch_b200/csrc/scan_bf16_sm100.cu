@@ -3,21 +3,24 @@
 // matrix never leaves the SM.  Replaces the sgemm + heap inside faiss IndexFlatIP.search
 // (test_amazon_filterd.py:211-214,578; fine_tune_ours.py:848-849,882).
 //
-// Shape of one CTA (persistent, 1 CTA per SM, 384 threads):
-//   warp 0 lane 0   TMA producer: loads its resident query m-tiles once, then streams DB tiles
-//                   (128 rows x d_pad bf16, SWIZZLE_128B, one 16 KB box per 64-wide K block) through an
-//                   mbarrier ring.
-//   warp 1 lane 0   MMA issuer: for every DB tile and every resident m-tile, num_kb*4 tcgen05.mma
-//                   (M=128 queries, N=128 rows, K=16) into one of four 128-column TMEM slots; commits
-//                   to the slot's "full" barrier, and to the stage's "empty" barrier after the last m-tile.
-//   warp 2          TMEM allocator (512 columns).
-//   warps 4-11      two epilogue warpgroups (slots 0/2 and 1/3).  A thread owns ONE query (TMEM lane):
-//                   tcgen05.ld 32 columns -> 3-input max tree -> one compare against the query's running
-//                   threshold.  Only when some lane of the warp sees max > thr does the warp take the slow
-//                   path: those lanes dump their 32 raw scores as a 144-byte HitRecord into the private
-//                   sub-region of (their query, this CTA, their warpgroup) — a register counter, no atomics.
-//                   refine (select.cu) turns a query's records into exact top-k lists and a tighter
-//                   threshold between waves.
+// Four kernels share one structure (persistent, 1 CTA per SM, 384 threads, warp-specialised) — DESIGN.md 3.1:
+//   scan_bf16_2cta_kernel   DEFAULT for d <= 128 and more than 128 queries: cluster (2,1,1), cta_group::2, M = 256
+//                           queries x N = 256 rows per MMA, each CTA loads half of every 256-row DB tile
+//   scan_bf16_ts_kernel     d <= 128, at most 128 queries (DB-stream bound): 1-CTA, query tiles live in TMEM
+//   scan_bf16_kernel        d <= 128, 1-CTA, both operands from shared memory (kept for A/B runs: SSS_SCAN_VARIANT=ss)
+//   scan_bf16_kloop_kernel  128 < d <= 4096: pair kernel with BOTH operands streamed per 64-wide K block
+// Roles inside a CTA:
+//   warp 0          TMA producer: resident query m-tiles once (or per K block), then DB tiles (128 rows x 64 columns
+//                   of bf16, SWIZZLE_128B, 16 KB boxes) through an mbarrier ring
+//   warp 1          MMA issuer (warp-uniform, one elected lane): tcgen05.mma kind::f16 into TMEM slots; commits to
+//                   the slot's "full" barrier and, after a tile's last m-tile, to the stage's "empty" barrier
+//   warp 2          TMEM allocator (512 columns)
+//   warps 4-11      two epilogue warpgroups.  A thread owns ONE query (TMEM lane): tcgen05.ld 32 columns -> 3-input
+//                   max tree -> one compare against the query's running threshold.  Only when some lane of the warp
+//                   sees max > thr does the warp take the slow path: those lanes dump their 32 raw scores as a
+//                   144-byte HitRecord into the private sub-region of (their query, this CTA or pair, their
+//                   warpgroup) — a register counter, no atomics.  refine (select.cu) turns a query's records into
+//                   exact top-k lists and a tighter threshold between waves.
 //
 // Arithmetic intensity: a CTA holding num_mt*128 resident queries does 2*num_mt*128*128*d_pad flop per
 // 128*d_pad*2 bytes of DB tile, i.e. num_mt*128 flop/byte — 512 flop/B at num_mt=4, well above the B200
