@@ -95,6 +95,7 @@ struct RefineCfg {
   static constexpr int kThreads = THREADS;
   static constexpr int kRmax = RMAX;             // max hit records per query and wave
   static constexpr bool kLast = LAST;            // nobody behind us: too-large inputs are an overflow
+  static constexpr int kTmpBytes = 1280;         // radix-select histogram (258 ints) / rank-sort staging (32 keys)
   static constexpr int kMaxSub = 512;            // max record sub-regions per query (2 * grid_x)
   // scratch = [recptr | subpre], reused as the gather/sort array A[kSlots] once the passes are done
   __host__ __device__ static constexpr size_t scratch_bytes() {
@@ -103,7 +104,7 @@ struct RefineCfg {
     return ((s > a ? s : a) + 15) / 16 * 16;
   }
   static constexpr size_t smem_bytes(int d_round, bool rescore) {
-    return scratch_bytes() + 4096 + (size_t)kSlots * 8 + (size_t)NC * 8 + 16 + (size_t)NC * 2 + (size_t)SURV * 2 +
+    return scratch_bytes() + kTmpBytes + (size_t)kSlots * 8 + (size_t)NC * 8 + 16 + (size_t)NC * 2 + (size_t)SURV * 2 +
            (size_t)KMAX * 2 + 8 + 16 + sizeof(float) * (rescore ? d_round : 0);
   }
 };
@@ -130,7 +131,7 @@ struct RefineSmem {
     recptr = reinterpret_cast<uint32_t*>(p);
     subpre = recptr + C::kRmax;
     tmp = reinterpret_cast<uint64_t*>(p + C::scratch_bytes());
-    unsigned char* rest = p + C::scratch_bytes() + 4096;
+    unsigned char* rest = p + C::scratch_bytes() + C::kTmpBytes;
     owner = reinterpret_cast<uint32_t*>(rest);
     best = owner + C::kSlots;
     ent_key = best + C::kSlots;
@@ -583,6 +584,8 @@ __global__ void __launch_bounds__(C::kThreads) refine_large_kernel(RefineArgs a,
   }
 }
 
+// (128-thread blocks, 7 per SM — every query of a 1000-query wave resident at once — measured 1 % slower:
+// profiles/r01_ab_experiments.md)
 using RefineSmall = RefineCfg<10, 1536, 768, 512, 8, 16, 256, 512, false>;
 using RefineLarge = RefineCfg<12, 4096, 4096, 2048, 16, 16, 512, 4096, true>;
 
