@@ -459,6 +459,8 @@ def main():
 
     peaks, peak_kind = measured_peaks()
     rows_local = int(seg[-1])
+    if a.reduce == "sum":  # linearity: the scan runs over the per-session summed rows
+        rows_local = len(seg) - 1
     flops_per_step = 2.0 * a.nq * rows_local * a.d
     scan_s = scan_ns[0] * 1e-9 / a.steps
     tensor_mode = a.mode in ("exact", "bf16")
