@@ -93,3 +93,43 @@ def test_flat_sessions_slice():
     whole = featurize.featurize_arrays(featurize.flatten(sess[10:30], featurize.QueryVocab()))
     for k in ("query_pos", "product_key", "product_pos", "qp_src", "pp_dst"):
         assert np.array_equal(part[k], whole[k])
+
+
+def test_featurize_batch_with_a_feature_cache_matches_collate_on_the_host():
+    """feature gather through the cache (device = cpu here): same node features, in the same node order, as
+    tokenising every node of every session and looking its feature up (the synthetic stand-in of the text model)"""
+    import torch
+    in_dim = 16
+    tok = synth.HashTokenizer()
+    sess = synth.make_sessions(60, 77)
+    sess[5] = [a for a in sess[5] if a[1] == 's'] or sess[5]
+
+    def feats(strings):
+        ids = tok(strings, padding='max_length', max_length=20, truncation=True, return_tensors="pt")['input_ids']
+        return synth.text_features(ids, in_dim)
+
+    vocab = featurize.QueryVocab()
+    flat = featurize.flatten(sess, vocab)
+    titles = {0: 'UNK'}
+    for s in sess:
+        for act in s:
+            if act[1] != sessions.SEARCH:
+                titles.setdefault(act[-1], act[-2] if act[-2] is not None else '')
+    item_ids = sorted(titles)
+    cache = featurize.FeatureCache(feats(sorted(vocab.ids, key=vocab.ids.get)), item_ids,
+                                   feats([titles[i] for i in item_ids]), "cpu")
+    got = featurize.featurize_batch(flat, cache)
+    graphs = [sessions.sequence_to_graph(0, s, s[:1], tok, 20) for s in sess]
+    for g in graphs:
+        g['query'].x = synth.text_features(g['query'].input_ids, in_dim)
+        g['product'].input_ids = synth.text_features(g['product'].input_ids, in_dim)
+    want = graph.collate(graphs)
+    assert torch.equal(got['query'].x, want['query'].x)
+    assert torch.equal(got['product'].input_ids, want['product'].input_ids)
+    assert torch.equal(got['product'].cnt, want['product'].cnt)
+    assert torch.equal(got.edge_index_dict[graph.EDGE_PQ], want.edge_index_dict[graph.EDGE_PQ])
+    assert got.num_graphs == want.num_graphs == 60
+    # an item without a cached feature is an error, not a silent zero row
+    small = featurize.FeatureCache(feats([""] * len(vocab)), item_ids[:3], feats(["x"] * 3), "cpu")
+    with pytest.raises(KeyError):
+        featurize.featurize_batch(flat, small)
