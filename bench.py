@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--d", type=int, default=128)
     ap.add_argument("--mode", default="exact", choices=["exact", "bf16", "fp32"])
     ap.add_argument("--reduce", default="max", choices=["max", "sum", "none"])
+    ap.add_argument("--metric", default="cos", choices=["cos", "l2"],
+                    help="cos = the headline (inner product over normalised rows); l2 = squared L2 over the same rows")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -257,7 +259,8 @@ def encoder_bench(device, no_cpu=False, n_sessions=2000, batch=200):
 
 def workload_config(a):
     return {"workload": "configs[2]: %d subsession rows (sessions of 1+Poisson(7) contiguous rows), d=%d, nq=%d, "
-                        "fused per-session %s + top-%d, cosine" % (a.rows, a.d, a.nq, a.reduce, a.k),
+                        "fused per-session %s + top-%d, %s" % (a.rows, a.d, a.nq, a.reduce, a.k,
+                                                               "cosine" if a.metric == "cos" else "squared L2"),
             "rows": a.rows, "d": a.d, "nq": a.nq, "k": a.k, "reduce": a.reduce, "mode": a.mode,
             "sharding": "rows/%d at session boundaries + 1 NCCL all-gather merge" % a.gpus if a.gpus > 1 else "none",
             "l2": "inputs larger than L2 (database %.2f GB bf16 per pass)" % (a.rows * a.d * 2 / 1e9)}
@@ -313,7 +316,8 @@ def main():
     row_off = int(lens_all[:s_lo].sum())
     g = torch.Generator(device=dev)
     g.manual_seed(4321 + shard_r)
-    inner = sss.IndexFlatIP(a.d, device=local_rank, id_offset=(s_lo if a.reduce != "none" else row_off), mode=a.mode)
+    index_cls = sss.IndexFlatL2 if a.metric == "l2" else sss.IndexFlatIP
+    inner = index_cls(a.d, device=local_rank, id_offset=(s_lo if a.reduce != "none" else row_off), mode=a.mode)
     lens_t = torch.from_numpy(lens).to(dev)
     host_rows = []
     chunk = 131072
@@ -332,7 +336,7 @@ def main():
     seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     if a.reduce != "none":
         inner.set_segments(seg, a.reduce)
-    index = ShardedIndex(inner, world_size=world, rank=rank) if world > 1 else inner
+    index = ShardedIndex(inner, world_size=world, rank=rank, metric=(1 if a.metric == "l2" else 0)) if world > 1 else inner
 
     # ---- queries: noisy copies of database sessions (a query subsession resembles its session) ------
     gq = torch.Generator(device=dev)
@@ -501,7 +505,7 @@ def main():
             pass
 
     cpu_baseline = None
-    if not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline and world == 1 and a.metric == "cos":
         from oracle import search_oracle as so
         cores = os.cpu_count() or 1
         hdb = np.concatenate(host_rows, axis=0)

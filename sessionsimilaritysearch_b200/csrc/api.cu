@@ -45,7 +45,7 @@ static void dev_free(T*& p) {
 struct Workspace {
   int64_t nq_pad = 0;
   int cap = 0, d = 0, d_pad = 0, k = 0;
-  float *thr = nullptr, *margin = nullptr, *q_f32 = nullptr, *out_D = nullptr;
+  float *thr = nullptr, *margin = nullptr, *qn2 = nullptr, *q_f32 = nullptr, *out_D = nullptr;
   uint32_t *cnt = nullptr, *nret = nullptr, *skip_list = nullptr, *skip_cnt = nullptr;
   uint64_t* cand = nullptr;
   int* flags = nullptr;  // [0] overflow, [1] kernel watchdog
@@ -66,7 +66,7 @@ struct Workspace {
       cap = std::max(cap_, cap);
       d = d_;
       d_pad = d_pad_;
-      if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&cnt, nq_pad) ||
+      if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&qn2, nq_pad) || dev_alloc(&cnt, nq_pad) ||
           dev_alloc(&nret, nq_pad) || dev_alloc(&skip_list, nq_pad) || dev_alloc(&skip_cnt, 2) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
         return 1;
       void* v = nullptr;
@@ -97,7 +97,7 @@ struct Workspace {
     return 0;
   }
   void release_query_side() {
-    dev_free(thr); dev_free(margin); dev_free(cnt); dev_free(nret); dev_free(skip_list); dev_free(skip_cnt); dev_free(cand); dev_free(q_f32);
+    dev_free(thr); dev_free(margin); dev_free(qn2); dev_free(cnt); dev_free(nret); dev_free(skip_list); dev_free(skip_cnt); dev_free(cand); dev_free(q_f32);
     if (q_bf16) cudaFree(q_bf16);
     q_bf16 = nullptr;
   }
@@ -109,7 +109,7 @@ struct Workspace {
   }
   SelectState state() const {
     SelectState s;
-    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.skip_list = skip_list; s.skip_cnt = skip_cnt;
+    s.thr = thr; s.cnt = cnt; s.nret = nret; s.cand = cand; s.margin = margin; s.qn2 = qn2; s.skip_list = skip_list; s.skip_cnt = skip_cnt;
     s.overflow = flags;
     s.cap = cap;
     return s;
@@ -205,11 +205,12 @@ extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric
   sss_index* ix = new sss_index();
   ix->device = device;
   ix->d = d;
-  ix->d_pad = (d + 63) / 64 * 64;
+  // (L2 on the tensor path keeps -||x||^2 / 2 in two extra bf16 columns, hi + lo: prep.cu add_rows_kernel)
+  ix->d_pad = (d + (metric == SSS_METRIC_L2 ? 2 : 0) + 63) / 64 * 64;
   ix->metric = metric;
   ix->id_offset = id_offset;
   ix->num_sms = prop.multiProcessorCount;
-  ix->tensor_ok = ix->d_pad <= 4096 && metric == SSS_METRIC_IP;
+  ix->tensor_ok = ix->d_pad <= 4096;
   *out = ix;
   return 0;
 }
@@ -286,7 +287,7 @@ extern "C" int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int 
     src = staged;
   }
   int rc = launch_add_rows(src, n, ix->d, ix->d_pad, norm_mode, ix->rows.f32, ix->rows.bf16, ix->rows.n,
-                           ix->rows.maxnorm2, st);
+                           ix->rows.maxnorm2, st, (ix->tensor_ok && ix->metric == SSS_METRIC_L2) ? 1 : 0);
   if (staged) {
     cudaStreamSynchronize(st);
     cudaFree(staged);
@@ -320,6 +321,8 @@ extern "C" int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, i
   if (dev_alloc(&ix->seg_off, n_seg + 1) || dev_alloc(&ix->row_seg, ix->rows.n)) return 1;
   SSS_CUDA_OK(cudaMemcpy(ix->seg_off, seg_off, (size_t)(n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
   if (launch_row_seg(ix->seg_off, n_seg, ix->row_seg, 0)) return 1;
+  SSS_REQUIRE(reduce != SSS_REDUCE_SUM || ix->metric == SSS_METRIC_IP,
+              "reduce = sum is defined for the inner-product metric only (a sum of distances is not a distance to a sum)");
   if (reduce == SSS_REDUCE_SUM) {
     // linearity: sum_r <q, x_r> = <q, sum_r x_r>; build the summed rows once, then search them as rows
     ix->sums.release();
@@ -399,10 +402,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   int mode = b.mode;
   if (mode != SSS_MODE_FP32 && !ix->tensor_ok) {
     SSS_REQUIRE(mode == SSS_MODE_EXACT,
-                "SSS_MODE_BF16 needs d <= 4096 and the inner-product metric (use SSS_MODE_EXACT or SSS_MODE_FP32)");
+                "SSS_MODE_BF16 needs d <= 4096 (d <= 4095 for L2); use SSS_MODE_EXACT or SSS_MODE_FP32");
     mode = SSS_MODE_FP32;  // EXACT is defined as "bit-identical to FP32": run the fp32 scan itself
   }
   const bool tensor = mode != SSS_MODE_FP32 && n_rows > 0;
+  const bool l2_tensor = tensor && ix->metric == SSS_METRIC_L2;
   ix->stat_variant = 0;
   const int cap = 4096;
   SSS_REQUIRE(b.k <= cap / 2, "k too large (max 2048)");
@@ -448,7 +452,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     SelectState state = ws.state();
     state.cap = cap;
     if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr,
-                            mode == SSS_MODE_EXACT ? 1 : 0, rs.maxnorm2, state, st))
+                            mode == SSS_MODE_EXACT ? 1 : 0, rs.maxnorm2, state, st, l2_tensor ? 1 : 0))
       return 1;
     SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
     ix->stat_kernels += 1;
@@ -522,6 +526,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ra.rec_cnt = cnt_buf;
       ra.rec_nsub = tensor ? plan.rec_nsub : 0;
       ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
+      ra.l2_tensor = l2_tensor ? 1 : 0;
       ra.lazy = (mode == SSS_MODE_EXACT && !safe && b.k <= 256 && !no_lazy) ? 1 : 0;
       ra.final = end == ends.back() ? 1 : 0;
       ra.row_limit = n_rows;
@@ -803,7 +808,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     RefineArgs ra;
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
-    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.lazy = 0; ra.final = 1; ra.row_limit = ix->n; ra.debug = nullptr;
+    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.l2_tensor = 0; ra.lazy = 0; ra.final = 1; ra.row_limit = ix->n; ra.debug = nullptr;
     std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
     int64_t begin = 0;
     for (int64_t end : ends) {

@@ -61,6 +61,7 @@ struct SelectState {
   uint32_t* nret;    // [nq_pad] entries [0, nret) are retained (already reduced) from earlier waves
   uint64_t* cand;    // [nq_pad, cap]
   float* margin;     // [nq_pad] filter slack of the bf16 scan in EXACT mode, else 0
+  float* qn2;        // [nq_pad] ||q||^2 (L2 metric on the tensor path: -dist = 2 * tensor score - ||q||^2)
   uint32_t* skip_list;  // [nq_pad] queries the small refine left to the large one (this wave)
   uint32_t* skip_cnt;   // [2] length of skip_list, indexed by wave parity
   int* overflow;     // [1] set when any list / record region overflowed

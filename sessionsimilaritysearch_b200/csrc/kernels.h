@@ -9,10 +9,10 @@ namespace sss {
 
 // prep.cu
 int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
-                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st);
+                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st, int aug = 0);
 // stats[0] = bits of max ||row||^2, stats[1] = bits of max ||row - bf16(row)||^2 (both from launch_add_rows)
 int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
-                        const unsigned int* stats, SelectState st, cudaStream_t stream);
+                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug = 0);
 int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st);
 int launch_segment_sum(const float* rows, const int64_t* seg_off, int64_t n_seg, int d, float* out, cudaStream_t st);
 int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, cudaStream_t st);
@@ -73,6 +73,8 @@ struct RefineArgs {
   const uint32_t* rec_cnt;   // [nq_pad * rec_nsub]
   int rec_nsub;              // record sub-regions per query (2 * scan grid_x)
   int rec_cap;               // records per sub-region (16; 64 for the K-loop scan)
+  int l2_tensor;             // L2 metric searched on the tensor path: thresholds live in tensor-score space
+                             // ((||q||^2 - dist) / 2), keys in -dist space; refine converts at the boundary
   int lazy;                  // EXACT mode: keep candidate rows with tensor-core keys, re-score in the last wave
   int final;                 // last wave of the search
   int64_t row_limit;         // rows >= row_limit in a record are TMA zero fill

@@ -13,10 +13,13 @@ namespace sss {
 __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__ in, int64_t n, int d, int d_pad,
                                                        int norm_mode, int rows_per_block, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16, int64_t out_row0,
-                                                       unsigned int* __restrict__ maxnorm2_bits) {
+                                                       unsigned int* __restrict__ maxnorm2_bits, int aug) {
+  // aug (L2 metric on the tensor path): bf16 columns d, d+1 of a row hold -||y||^2 / 2 (hi + lo) and the query side 1, 1, so
+  // that the tensor-core score is <q, y> - ||y||^2 / 2 = (||q||^2 - ||q - y||^2) / 2 — ordered like -distance.
   extern __shared__ float smem[];
   const int ld = d + 1;
   float* den = smem + (size_t)rows_per_block * ld;
+  float* caug = den + rows_per_block;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   const int nrows = (int)min((int64_t)rows_per_block, n - row0);
   const int tid = threadIdx.x;
@@ -41,11 +44,24 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
     den[tid] = dn;
     if (maxnorm2_bits) {
       // ||x - bf16(x)||^2 of the stored row: the exact rounding error the tensor-core scan will see
-      float e2 = 0.0f;
+      float e2 = 0.0f, n2y = 0.0f;
       for (int j = 0; j < d; ++j) {
         const float y = norm_mode == 0 ? x[j] : __fdiv_rn(x[j], dn);
         const float r = y - __bfloat162float(__float2bfloat16_rn(y));
         e2 = __fmaf_rn(r, r, e2);
+        n2y = __fmaf_rn(y, y, n2y);
+      }
+      if (aug) {
+        // -||y||^2 / 2 in TWO bf16 columns (hi + lo: 16 mantissa bits — one column would put 2^-9 * ||y||^2 / 2 of
+        // rounding error into every score, far more than the rest of the slack for unnormalised rows)
+        const float c = -0.5f * n2y;
+        caug[tid] = c;
+        const float chi = __bfloat162float(__float2bfloat16_rn(c));
+        const float clo = __bfloat162float(__float2bfloat16_rn(c - chi));
+        // what is left: the split residual + the fp32 rounding of ||y||^2 itself
+        const float ec = fabsf(c - chi - clo) + (float)(d + 8) * 1.2e-7f * fabsf(c);
+        e2 = __fmaf_rn(ec, ec, e2);
+        n2 = n2 + chi * chi + clo * clo;
       }
       atomicMax(maxnorm2_bits, __float_as_uint(n2 * 1.00002f + 1e-30f));
       atomicMax(maxnorm2_bits + 1, __float_as_uint(e2 * 1.00002f + 1e-30f));
@@ -69,6 +85,10 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
       if (j < d) {
         v = smem[r * ld + j];
         if (norm_mode != 0) v = __fdiv_rn(v, den[r]);
+      } else if (aug && j == d) {
+        v = caug[r];
+      } else if (aug && j == d + 1) {
+        v = caug[r] - __bfloat162float(__float2bfloat16_rn(caug[r]));
       }
       dstb[i] = __float2bfloat16_rn(v);
     }
@@ -76,17 +96,19 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
 }
 
 int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
-                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st) {
+                    int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st, int aug) {
+  SSS_REQUIRE(!aug || (out_bf16 != nullptr && maxnorm2_bits != nullptr && d_pad >= d + 2),
+              "add_rows: the L2 columns need the bf16 copy, its statistics and two spare columns");
   if (n <= 0) return 0;
   int rpb = (int)(60 * 1024 / (sizeof(float) * (d + 1)));
   if (rpb > 128) rpb = 128;
   if (rpb < 1) rpb = 1;
-  size_t smem = sizeof(float) * ((size_t)rpb * (d + 1) + rpb);
+  size_t smem = sizeof(float) * ((size_t)rpb * (d + 1) + 2 * (size_t)rpb);
   SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for add_rows_kernel");
   SSS_CUDA_OK(cudaFuncSetAttribute(add_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (n + rpb - 1) / rpb;
   add_rows_kernel<<<(unsigned)blocks, 128, smem, st>>>(in, n, d, d_pad, norm_mode, rpb, out_f32,
-                                                        (__nv_bfloat16*)out_bf16, out_row0, maxnorm2_bits);
+                                                        (__nv_bfloat16*)out_bf16, out_row0, maxnorm2_bits, aug);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -102,7 +124,7 @@ int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode,
 // core.  This is a rigorous bound, about 2.3x tighter than 2^-7 * ||q|| * ||x||.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad, int d, int d_pad,
                                     __nv_bfloat16* __restrict__ q_bf16, int exact, const unsigned int* stats,
-                                    SelectState st) {
+                                    SelectState st, int aug) {
   const int warps_per_block = blockDim.x / 32;
   const int64_t row = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -110,9 +132,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int
   float ss = 0.0f, ee = 0.0f;
   for (int j = lane; j < d_pad; j += 32) {
     float v = (row < nq && j < d) ? q[row * (int64_t)d + j] : 0.0f;
+    const bool one = aug && (j == d || j == d + 1) && row < nq;  // L2 on the tensor path: query side of the extra columns
+    if (one) v = 1.0f;
     const __nv_bfloat16 vb = __float2bfloat16_rn(v);
     const float r = v - __bfloat162float(vb);
-    ss += v * v;
+    if (!one) ss += v * v;
     ee += r * r;
     if (q_bf16) q_bf16[row * (int64_t)d_pad + j] = vb;
   }
@@ -125,10 +149,13 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int
     if (exact && stats != nullptr) {
       const float xn = sqrtf(__uint_as_float(stats[0]));   // max ||x||   (inflated at add time)
       const float xe = sqrtf(__uint_as_float(stats[1]));   // max ||x - x^||
-      const float qn = sqrtf(ss * 1.0001f), qe = sqrtf(ee * 1.0001f);
+      const float qn = sqrtf((ss + (aug ? 2.0f : 0.0f)) * 1.0001f), qe = sqrtf(ee * 1.0001f);
       m = (qn * xe + qe * (xn + xe)) * 1.0001f + (float)d * 5.4e-7f * qn * xn + 1e-30f;
+      // (the conversion -dist = 2 * score - ||q||^2 uses this kernel's own ||q||^2: its rounding is part of the slack)
+      if (aug) m += 4e-7f * (ss + 2.0f);
     }
     st.margin[row] = m;
+    if (st.qn2 != nullptr) st.qn2[row] = ss;
     st.thr[row] = row < nq ? -INFINITY : INFINITY;
     st.cnt[row] = 0;
     st.nret[row] = 0;
@@ -141,11 +168,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int
 }
 
 int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
-                        const unsigned int* stats, SelectState st, cudaStream_t stream) {
+                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug) {
   const int wpb = 8;
   int64_t blocks = (nq_pad + wpb - 1) / wpb;
   prep_queries_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(q, nq, nq_pad, d, d_pad, (__nv_bfloat16*)q_bf16,
-                                                                  exact, stats, st);
+                                                                  exact, stats, st, aug);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

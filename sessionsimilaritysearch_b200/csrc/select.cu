@@ -201,8 +201,15 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
   const int nr = lazy ? 0 : nr_all;   // retained exact entries
   const int nl = lazy ? nr_all : 0;   // retained lazy rows
   uint64_t* g = st.cand + (size_t)q * st.cap;
-  const float margin = st.margin[q];
-  const float thr = st.thr[q];
+  // L2 on the tensor path: the scan (and st.thr, st.margin) live in tensor-score space, score = (||q||^2 - dist) / 2;
+  // keys, the retained lists and every comparison below live in -dist space: key value = 2 * score - ||q||^2, slack
+  // doubled.  Thresholds are converted back (rounded down) when they are published.
+  const bool l2t = a.l2_tensor != 0;
+  const float qn2 = l2t ? st.qn2[q] : 0.0f;
+  const float thr_scan = st.thr[q];
+  const float margin = l2t ? 2.0f * st.margin[q] : st.margin[q];
+  const float thr = l2t ? __fmaf_rn(2.0f, thr_scan, -qn2) : thr_scan;
+  auto to_scan = [&](float t) { return l2t ? __fmul_rd(0.5f, __fadd_rd(t, qn2)) : t; };
   const int d_round = (a.d + C::kKc - 1) / C::kKc * C::kKc;
 
   __syncthreads();  // previous query of a persistent block is fully done with shared memory
@@ -276,10 +283,10 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         for (int i = 0; i < 8; ++i) x[i] = rv[i];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          mask |= (__uint_as_float(x[i].x) > thr ? 1u : 0u) << (4 * i);
-          mask |= (__uint_as_float(x[i].y) > thr ? 1u : 0u) << (4 * i + 1);
-          mask |= (__uint_as_float(x[i].z) > thr ? 1u : 0u) << (4 * i + 2);
-          mask |= (__uint_as_float(x[i].w) > thr ? 1u : 0u) << (4 * i + 3);
+          mask |= (__uint_as_float(x[i].x) > thr_scan ? 1u : 0u) << (4 * i);
+          mask |= (__uint_as_float(x[i].y) > thr_scan ? 1u : 0u) << (4 * i + 1);
+          mask |= (__uint_as_float(x[i].z) > thr_scan ? 1u : 0u) << (4 * i + 2);
+          mask |= (__uint_as_float(x[i].w) > thr_scan ? 1u : 0u) << (4 * i + 3);
         }
         const int64_t room = a.row_limit - (int64_t)row_base;  // rows past the end of the index (last tile)
         if (room < 32) mask = room <= 0 ? 0u : (mask & ((1u << (int)room) - 1u));
@@ -298,7 +305,8 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1u;
         if (pos < C::kNc) {
-          sm.ent_key[pos] = score_key(r->v[bit]);
+          const float v = r->v[bit];
+          sm.ent_key[pos] = score_key(l2t ? __fmaf_rn(2.0f, v, -qn2) : v);
           sm.ent_row[pos] = row_base + (uint32_t)bit;
         }
         ++pos;
@@ -450,7 +458,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
         if (tid == 0) {
           st.cnt[q] = (uint32_t)nsurv;
           st.nret[q] = nsurv > 0 ? ((uint32_t)nsurv | 0x80000000u) : 0u;
-          st.thr[q] = new_thr;
+          st.thr[q] = fmaxf(thr_scan, to_scan(new_thr));  // (never lower it: the conversion rounds down)
           if (a.debug != nullptr) {
             atomicAdd(&a.debug[0], (unsigned long long)n_ent);
             atomicAdd(&a.debug[2], (unsigned long long)(sm.ctr[3] & 0x3FFFFFFF));
@@ -556,7 +564,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     st.cnt[q] = m;
     st.nret[q] = m;
     // thresholds only ever rise (a bootstrap threshold may already be in place while fewer than k sessions passed)
-    st.thr[q] = m == a.k ? fmaxf(new_thr, key_score(cand_key(sm.A[a.k - 1])) - margin) : new_thr;
+    st.thr[q] = fmaxf(thr_scan, to_scan(m == a.k ? fmaxf(new_thr, key_score(cand_key(sm.A[a.k - 1])) - margin) : new_thr));
   }
   return RF_DONE;
 }

@@ -299,6 +299,35 @@ def test_full_record_subregion_retries_with_more_room_not_the_safe_schedule(sss,
     _assert_exact(D3, I3, D2, I2)
 
 
+@pytest.mark.parametrize("d,n,nq,seg_mean", [(64, 300000, 200, 0), (128, 300000, 70, 7), (96, 40000, 300, 0)])
+def test_l2_on_the_tensor_path(sss, oracle, d, n, nq, seg_mean):
+    """squared-L2 search through the tensor-core scan: the bf16 rows carry -||x||^2 / 2 in one extra column (d = 128
+    therefore takes the K-loop kernel), thresholds live in tensor-score space and keys in -distance space.  exact mode
+    must equal the fp32 mode bit for bit (distances ascending, ties by id), also with a per-session min."""
+    rng = np.random.default_rng(61)
+    db = (make_iid(n, d, 62) * rng.uniform(0.8, 1.25, size=(n, 1))).astype(np.float32)   # norms matter for L2
+    q = make_iid(nq, d, 63)
+    ix = sss.build_index(db, 'l2', mode="exact")
+    seg = None
+    if seg_mean:
+        seg = make_segments(n, 64, mean=seg_mean)
+        ix.set_segments(seg, "max")     # max of -distance = the session's nearest row
+    D, I = ix.search(q, 50)
+    st = ix.stats()
+    assert st["scan_variant"] in ("ts", "2cta", "kloop") and st["reruns"] == 0, (st["scan_variant"], st["reruns"],
+                                                                                st["overflow_reason"], st["waves"])
+    assert (st["scan_variant"] == "kloop") == (d == 128)
+    D2, I2 = ix.search(q, 50, mode="fp32")
+    _assert_exact(D, I, D2, I2)
+    assert np.all(np.diff(D, axis=1) >= 0) and np.all(D >= 0)
+    sub = np.arange(0, nq, max(1, nq // 3))[:3]
+    Do, Io = oracle.search_flat(db, q[sub], 50, metric=oracle.METRIC_L2, seg_off=seg, reduce=1 if seg is not None else 0)
+    _assert_exact(D[sub], I[sub], Do, Io)
+    Db, Ib = ix.search(q, 50, mode="bf16")
+    recall = np.mean([len(set(Ib[r]) & set(I[r])) / 50.0 for r in range(nq)])
+    assert recall >= 0.95 and np.max(np.abs(Db - D) / (1.0 + D)) <= 2e-2, recall
+
+
 def test_torch_device_tensors(sss, oracle):
     import torch
     db = make_iid(10000, 128, 21)
