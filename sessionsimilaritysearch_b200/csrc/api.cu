@@ -427,7 +427,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   const bool overlap = tensor && ov && ov[0] == '1';
   if (tensor) {
     // leave shared memory for the refine blocks that co-run with the scan when overlapping
-    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost)) return 1;
+    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost,
+                       ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0))) return 1;
     if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
     ix->stat_variant = plan.kloop ? 4 : plan.two_cta ? 3 : plan.ts ? 2 : 1;
     if (overlap && !ix->side) {
@@ -446,7 +447,8 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   bool safe = false;
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (tensor && plan.rec_cap != (plan.kloop ? 4 : 1) * kRecSubCap * ix->rec_boost) {
-      if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost)) return 1;
+      if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost,
+                       ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0))) return 1;
       if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
     }
     SelectState state = ws.state();

@@ -38,9 +38,12 @@ struct Bf16ScanPlan {
   int tile_rows;    // DB rows per tile (128, 256 for the 2-CTA variant, 512 for the K-loop variant)
   bool kloop;       // wide rows (d_pad > 128): both operands streamed per K block, one query group per CTA pair
   int groups;       // K-loop variant: query groups of 256
+  int last_k4;      // K-loop variant: 16-wide slices of real columns in the last K block
 };
 // rec_boost multiplies the records per sub-region (1, or 4 after a search that overflowed one)
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost = 1);
+// d_used = columns that hold data (d, + 2 for L2); 0 = d_pad
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost = 1,
+                   int d_used = 0);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,

@@ -54,6 +54,7 @@ struct ScanParams {
   float* cmax;           // bootstrap mode: write the max of every 32-row chunk to cmax[chunk * nq_pad + q] instead
                          // of filtering (chunk counted from row_begin)
   int groups;            // K-loop variant: query groups of 256 (one per CTA pair)
+  int last_k4;           // K-loop variant: 16-wide slices of real columns in the last K block (1..4)
 };
 
 template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
@@ -872,11 +873,15 @@ scan_bf16_kloop_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           const uint64_t adesc = umma_desc_sw128(sbase);
           const uint64_t b0desc = umma_desc_sw128(sbase + kKBlockBytes);
           const uint64_t b1desc = umma_desc_sw128(sbase + 2 * kKBlockBytes);
+          // the last K block may hold fewer than four 16-wide slices of real columns (the rest is zero padding)
+          const int n4 = kb + 1 == p.num_kb ? p.last_k4 : 4;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t acc = (kb | k4) != 0 ? 1u : 0u;
-            umma_bf16_2cta(tmem_base, adesc + (uint64_t)(2 * k4), b0desc + (uint64_t)(2 * k4), acc);
-            umma_bf16_2cta(tmem_base + 256u, adesc + (uint64_t)(2 * k4), b1desc + (uint64_t)(2 * k4), acc);
+            if (k4 < n4) {
+              const uint32_t acc = (kb | k4) != 0 ? 1u : 0u;
+              umma_bf16_2cta(tmem_base, adesc + (uint64_t)(2 * k4), b0desc + (uint64_t)(2 * k4), acc);
+              umma_bf16_2cta(tmem_base + 256u, adesc + (uint64_t)(2 * k4), b1desc + (uint64_t)(2 * k4), acc);
+            }
           }
           umma_commit_2cta(empty_bar + 8 * stage);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -1001,12 +1006,17 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
   return 0;
 }
 
-int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost) {
+int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost,
+                   int d_used) {
   SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 4096, "tensor-core scan supports d <= 4096");
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
   plan->kloop = false;
   plan->groups = 0;
+  {
+    const int tail = (d_used > 0 ? d_used : d_pad) - (d_pad - 64);  // real columns of the last K block
+    plan->last_k4 = tail <= 0 ? 4 : (tail + 15) / 16 > 4 ? 4 : (tail + 15) / 16;
+  }
   if (d_pad > 128) {
     // wide rows: the K-loop pair kernel (both operands streamed per K block)
     const int G = (total_mtiles + 1) / 2;
@@ -1113,6 +1123,7 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.q_bf16 = (const uint4*)q_bf16;
   p.cmax = cmax;
   p.groups = plan.groups;
+  p.last_k4 = plan.last_k4;
   {
     const char* dbg = getenv("SSS_SCAN_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
