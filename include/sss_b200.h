@@ -190,6 +190,12 @@ enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1, SSS_ENCODER_MATH_
 int sss_encoder_set_math(sss_encoder_t* enc, int math);
 int sss_encoder_get_math(const sss_encoder_t* enc);
 
+/* Row gather on the device: out[i, :] = table[ids[i], :] (fp32 [n_rows, d], int64 ids [n], out [n, d]).  Replaces the
+ * nn.Embedding lookup of NodeAsinEmbedding.forward (model/NodeEmbedding.py:137-138) and serves the text-feature cache
+ * of the batched featuriser.  An id outside [0, n_rows) fails with torch's own message ("index out of range in self"). */
+int sss_gather_rows(const float* table, int64_t n_rows, int d, const int64_t* ids, int64_t n, float* out, int device,
+                    void* stream);
+
 /* ---- batched host featuriser (replaces the per-session Python of sequence_to_graph, util_amazon_filtered.py:98-230,
  * followed by PyG's Batch.from_data_list, test_amazon_filterd.py:485-488, for what the encoder reads) ---------- */
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "sss_encoder_destroy": (c_int, [c_vp]),
     "sss_encoder_set_param": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_int, c_vp]),
     "sss_encoder_forward": (c_int, [c_vp, ctypes.POINTER(GraphBatch), c_vp, c_vp, c_vp]),
+    "sss_gather_rows": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_int, c_vp]),
     "sss_featurize_sizes": (c_int, [ctypes.POINTER(FlatSessions), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "sss_featurize_batch": (c_int, [ctypes.POINTER(FlatSessions), c_i64, ctypes.POINTER(GraphArrays), c_int]),

@@ -656,6 +656,27 @@ extern "C" int sss_normalize(const float* in, float* out, int64_t n, int d, int 
   return rc;
 }
 
+extern "C" int sss_gather_rows(const float* table, int64_t n_rows, int d, const int64_t* ids, int64_t n, float* out,
+                               int device, void* stream) {
+  SSS_REQUIRE(n_rows >= 0 && d >= 1 && n >= 0, "sss_gather_rows: bad shape");
+  if (n == 0) return 0;
+  SSS_REQUIRE(table && out && ids, "sss_gather_rows: NULL buffer");
+  DeviceGuard g(device);
+  SSS_REQUIRE(g.ok, "sss_gather_rows: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* bad = nullptr;
+  if (dev_alloc(&bad, 1)) return 1;
+  int host_bad = 0, rc = 0;
+  if (cudaMemsetAsync(bad, 0, sizeof(int), st) != cudaSuccess) rc = 1;
+  if (!rc) rc = launch_gather_rows(table, n_rows, d, ids, n, out, bad, st);
+  if (!rc && cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+  cudaFree(bad);
+  if (rc && g_err.empty()) set_error("sss_gather_rows: CUDA call failed");
+  SSS_REQUIRE(rc != 0 || host_bad == 0, "index out of range in self");   // torch.nn.Embedding's message
+  return rc;
+}
+
 extern "C" int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_shards, int64_t nq, int k, int metric,
                               float* D, int64_t* I, int device, void* stream) {
   SSS_REQUIRE(cand_D && cand_I && D && I, "sss_topk_merge: NULL buffer");

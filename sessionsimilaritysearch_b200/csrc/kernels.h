@@ -13,6 +13,8 @@ int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode,
 // stats[0] = bits of max ||row||^2, stats[1] = bits of max ||row - bf16(row)||^2 (both from launch_add_rows)
 int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
                         const unsigned int* stats, SelectState st, cudaStream_t stream, int aug = 0);
+int launch_gather_rows(const float* table, int64_t n_rows, int d, const int64_t* ids, int64_t n, float* out, int* bad,
+                       cudaStream_t st);
 int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st);
 int launch_segment_sum(const float* rows, const int64_t* seg_off, int64_t n_seg, int d, float* out, cudaStream_t st);
 int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, cudaStream_t st);

@@ -212,4 +212,38 @@ int launch_normalize(const float* in, float* out, int64_t n, int d, int norm_mod
   return launch_add_rows(in, n, d, d, norm_mode, out, nullptr, 0, nullptr, st);
 }
 
+// ---- row gather: out[i, :] = table[ids[i], :] ------------------------------------------------------------
+// nn.Embedding lookup (NodeAsinEmbedding.forward, model/NodeEmbedding.py:137-138) and the feature-cache gather of the
+// batched featuriser.  One warp per output row, 16-byte accesses when the rows allow it; an id outside the table
+// sets *bad (no silent clamping).
+__global__ void gather_rows_kernel(const float* __restrict__ table, int64_t n_rows, int d, const int64_t* __restrict__ ids,
+                                   int64_t n, float* __restrict__ out, int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (i >= n) return;
+  const int lane = threadIdx.x % 32;
+  const int64_t id = ids[i];
+  if (id < 0 || id >= n_rows) {
+    if (lane == 0) *bad = 1;
+    return;
+  }
+  const float* src = table + id * (int64_t)d;
+  float* dst = out + i * (int64_t)d;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int j = lane; j < d / 4; j += 32) d4[j] = __ldg(s4 + j);
+  } else {
+    for (int j = lane; j < d; j += 32) dst[j] = __ldg(src + j);
+  }
+}
+
+int launch_gather_rows(const float* table, int64_t n_rows, int d, const int64_t* ids, int64_t n, float* out, int* bad,
+                       cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int wpb = 8;
+  gather_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(table, n_rows, d, ids, n, out, bad);
+  SSS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace sss

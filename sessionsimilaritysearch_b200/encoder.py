@@ -129,3 +129,30 @@ class BinarizeHead:
                                           self.weight.shape[1], self.weight.shape[0], out.data_ptr(), self.device,
                                           _lib.current_stream(self.device)))
         return out
+
+
+def gather_rows(table, ids):
+    """table[ids] on the device through sss_gather_rows (CUDA tensors: fp32 [n_rows, d], int64 [n])"""
+    lib = _lib.load()
+    dev = table.device
+    if dev.type != "cuda":
+        raise RuntimeError("gather_rows runs on a CUDA device (no CPU fallback)")
+    table = table.contiguous()
+    ids = ids.to(device=dev, dtype=torch.int64).contiguous()
+    out = torch.empty((ids.shape[0], table.shape[1]), dtype=torch.float32, device=dev)
+    check(lib.sss_gather_rows(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), ids.shape[0],
+                              out.data_ptr(), dev.index, _lib.current_stream(dev.index)))
+    return out
+
+
+class NodeAsinEmbedding:
+    """the reference's per-product id embedding (model/NodeEmbedding.py:128-138): forward(ids) = weight[ids].
+    Its output is discarded on the configured path (use_id_embedding=False, model/model.py:288-291); kept for
+    drop-in completeness."""
+
+    def __init__(self, weight, device=None):
+        self.device = _lib.current_device() if device is None else int(device)
+        self.weight = _f32(weight, torch.device("cuda", self.device))
+
+    def __call__(self, ids):
+        return gather_rows(self.weight, torch.as_tensor(ids))

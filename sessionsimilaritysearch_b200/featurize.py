@@ -133,16 +133,22 @@ def featurize_batch(flat, cache, root_query_key=0, n_threads=0):
     def t(x):
         return torch.from_numpy(x).to(dev, non_blocking=True)
 
+    def rows(table, idx):  # feature gather: the library's kernel on the device, plain indexing for a host cache
+        if table.device.type == "cuda":
+            from .encoder import gather_rows
+            return gather_rows(table, idx)
+        return table.index_select(0, idx)
+
     out = SessionBatch()
     out.num_graphs = a["n_graphs"]
     q = out["query"]
-    q.x = cache.query_features.index_select(0, t(a["query_key"]))
+    q.x = rows(cache.query_features, t(a["query_key"]))
     q.pos_emb_id = t(a["query_pos"])
     q.batch = t(a["query_batch"])
     q.num_nodes = len(a["query_key"])
     p = out["product"]
     p.x = t(a["product_key"])
-    p.input_ids = cache.item_features.index_select(0, t(cache.item_rows(a["product_key"])))
+    p.input_ids = rows(cache.item_features, t(cache.item_rows(a["product_key"])))
     p.cnt = t(a["product_cnt"])
     p.pos_emb_id = t(a["product_pos"])
     p.batch = t(a["product_batch"])

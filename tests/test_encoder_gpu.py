@@ -146,6 +146,22 @@ def test_encoder_bf16x3_tcgen05_linears_match_fp32(shape):
     assert np.array_equal(enc(data).cpu().numpy(), out32)
 
 
+def test_gather_rows_and_id_embedding():
+    """sss_gather_rows = nn.Embedding lookup (NodeAsinEmbedding, model/NodeEmbedding.py:137-138): bit-equal to torch
+    indexing, odd widths included, out-of-range ids rejected with torch's message"""
+    import torch
+    import sessionsimilaritysearch_b200 as sss
+    g = torch.Generator().manual_seed(1)
+    for n_rows, d, n in ((1000, 200, 777), (50, 7, 33), (391, 768, 5)):
+        table = torch.randn((n_rows, d), generator=g)
+        ids = torch.randint(0, n_rows, (n,), generator=g)
+        emb = sss.NodeAsinEmbedding(table)
+        assert torch.equal(emb(ids).cpu(), table[ids])
+    with pytest.raises(RuntimeError, match="index out of range"):
+        emb(torch.tensor([0, 391]))
+    assert emb(torch.zeros(0, dtype=torch.int64)).shape == (0, 768)
+
+
 def test_nan_input_raises_like_the_reference():
     import sessionsimilaritysearch_b200 as sss
     from sessionsimilaritysearch_b200 import graph, sessions
