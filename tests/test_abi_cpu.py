@@ -64,3 +64,33 @@ def test_built_sass_is_blackwell_native(built_lib):
     assert "sm_100a" in out or "SM100a" in out.upper().replace("_", "")
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in out, mnemonic + " missing from SASS"
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (Python or CUDA) may import, link or execute it, and
+    there is no CPU fallback — the façade raises when the CUDA library is missing."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "sessionsimilaritysearch_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+            # imports, includes, dlopen / subprocess of anything under oracle/ (mentions in comments are fine)
+            if re.search(r"^\s*(from|import)\s+oracle\b|^\s*#\s*include\s*[<\"][^>\"]*oracle|dlopen\([^)]*oracle|"
+                         r"(subprocess|os\.system)[^\n]*oracle", text, re.M):
+                offenders.append(os.path.relpath(os.path.join(dirpath, f), root))
+    assert offenders == [], offenders
+    from sessionsimilaritysearch_b200 import _lib
+    saved, _lib._lib, _lib.LIB_PATH = (_lib._lib, _lib.LIB_PATH), None, os.path.join(pkg, "no_such_library.so")
+    try:
+        import pytest
+        with pytest.raises(RuntimeError, match="no\\s+CPU fallback"):
+            _lib.load()
+    finally:
+        _lib._lib, _lib.LIB_PATH = saved
