@@ -12,6 +12,10 @@
  *   faiss.IndexBinaryFlat             fine_tune_ours.py:839-843,871-876 -> sss_binary_*
  *   get_prediction_by_knn             test_amazon_filterd.py:59-78     -> sss_item_vote
  *   encoder(data) (GNN + pooling)     model/model.py:279-351, model/gnn.py:64-81,193-217 -> sss_encoder_*
+ *   gnn(x_dict, edge_index_dict), pooling(node_emb, data), get_node=True       -> sss_encoder_forward_ex
+ *   text embedder's masked mean       model/NodeEmbedding.py:112-125   -> sss_masked_mean
+ *   F.normalize(a) @ F.normalize(b).T fine_tune_ours.py:133,480,494    -> sss_cosine_matrix
+ *   get_score / get_ave_score         fine_tune_ours.py:42-97,883-897  -> sss_pair_scores, sss_seqratio_pairs
  *
  * Conventions
  *   - every entry point returns 0 on success, non-zero on failure; sss_last_error() then returns a
@@ -23,7 +27,11 @@
  *     default stream).  Host-buffer calls synchronise that stream before returning (their results are
  *     on the host); device-buffer search calls synchronise it only to read back an 8-byte status word
  *     (candidate-list overflow -> automatic rerun with a safe schedule; kernel watchdog).
- *   - handles are not thread-safe; one handle per GPU for row-sharded search.
+ *   - a search is replayed from a CUDA graph captured on its first call with a given (nq, k, mode); add /
+ *     set_segments drop the captured graphs.  Tuning knobs (SSS_WAVE_GROWTH, SSS_WAVE_FIRST, SSS_NO_BOOTSTRAP,
+ *     SSS_NO_LAZY, SSS_NO_GRAPH, SSS_SCAN_VARIANT) are read from the environment ONCE, when a handle is created.
+ *   - handles are not thread-safe; one handle per GPU for row-sharded search (several handles on several GPUs
+ *     may live in one process).
  *   - there is no CPU fallback anywhere behind this ABI.
  */
 #ifndef SSS_B200_H
@@ -54,7 +62,10 @@ enum {
 enum {
   SSS_MODE_EXACT = 0, /* tcgen05 bf16 filter + fixed-order fp32 rescoring: ids and scores bit-identical to FP32 */
   SSS_MODE_FP32 = 1,  /* CUDA-core fixed-order fp32 FMA scan (k-ascending), the bit-faithful restatement */
-  SSS_MODE_BF16 = 2   /* tcgen05 bf16 x bf16 -> fp32 scores returned as computed by the tensor core */
+  SSS_MODE_BF16 = 2   /* tcgen05 bf16 filter with a STATISTICAL slack (4 standard deviations of the bf16 rounding noise,
+                         never more than EXACT's rigorous bound) + the same fp32 rescoring of what passes: returned
+                         scores are fixed-order fp32, recall@k >= 0.999 against FP32 on embedding-like rows; up to
+                         ~10x fewer rows re-scored than EXACT at d = 1600 */
 };
 
 /* per-session reduction of subsession (row) scores; segments are contiguous row ranges */
@@ -78,8 +89,10 @@ int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int rows_on_dev
 
 /* Declare contiguous segments (sessions): seg_off[n_seg+1] (host, int64), seg_off[0]==0,
  * seg_off[n_seg]==ntotal.  reduce = MAX: score(session) = max over its rows; SUM: sum over its rows
- * (computed as <q, sum of rows>, rows summed in row order).  Returned ids are then session indices. */
-int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce);
+ * (computed as <q, sum of rows>, rows summed in row order).  Returned ids are then session indices.
+ * `stream` must be the stream the rows were added on (or one ordered after it); the call returns after it has
+ * drained.  A rejected call leaves the index unchanged. */
+int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce, void* stream);
 
 int64_t sss_index_ntotal(const sss_index_t* ix);
 int sss_index_dim(const sss_index_t* ix);
@@ -90,13 +103,21 @@ int sss_index_dim(const sss_index_t* ix);
 int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
                      float* D, int64_t* I, int out_on_device, void* stream);
 
+/* Top-k search of one row shard for the sharded path: the same search, results written as ONE packed device block
+ * [ids int64 nq*k | scores fp32 nq*k] of sss_packed_bytes(nq, k) bytes — the unit every rank contributes to the
+ * single all-gather; sss_topk_merge_packed consumes the gathered blocks as they are. */
+int64_t sss_packed_bytes(int64_t nq, int k);
+int sss_index_search_packed(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
+                            void* packed, void* stream);
+
 /* Counters of the last search on this handle.  what: 0 = kernels launched, 1 = scan waves,
- * 2 = overflow reruns, 3 = scan-kernel device time in ns, 4 = scan-kernel launches (3 and 4 need
- * sss_index_set_profiling(ix, 1): CUDA events are then recorded around every scan launch on the caller's
- * stream), 5..23 = refine volumes / phase cycles / scan role counters of profiling builds, 24 = bit mask of
- * what overflowed when the last search had to be redone with the safe schedule (1 record sub-region,
- * 2 records per query, 4 candidate list, 8 new candidates, 16 session table, 32 re-score list),
- * 25 = scan kernel of the last search (0 fp32 CUDA cores, 1 SS, 2 TS, 3 pair, 4 K-loop pair). */
+ * 2 = overflow reruns, 3 = scan-kernel device time in ns, 4 = scan-kernel launches, 5..8 = refine volumes
+ * (candidates, rows re-scored, sessions sorted, refine invocations) — 3..8 need sss_index_set_profiling(ix, 1):
+ * the search then runs as plain launches with CUDA events around every scan launch on the caller's stream instead of
+ * replaying its captured graph —, 24 = bit mask of what overflowed when the last search had to be redone (1 record
+ * sub-region, 2 records per query, 4 candidate list, 8 new candidates, 16 session table, 32 re-score list),
+ * 25 = scan kernel of the last search (0 fp32 CUDA cores, 1 SS, 2 TS, 3 pair, 4 K-loop pair), 26 = 1 when the last
+ * search replayed a captured CUDA graph.  Anything else: -1. */
 int64_t sss_index_stat(const sss_index_t* ix, int what);
 int sss_index_set_profiling(sss_index_t* ix, int on);
 
@@ -109,6 +130,10 @@ int sss_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, 
  * sss_index_search; ids < 0 are padding. */
 int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_shards, int64_t nq, int k, int metric,
                    float* D, int64_t* I, int device, void* stream);
+/* The same merge over n_shards packed blocks laid end to end (the output of all-gathering sss_index_search_packed
+ * blocks).  Limit of both forms: n_shards * k <= 8192 (one shared-memory sort per query). */
+int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k, int metric, float* D, int64_t* I,
+                          int device, void* stream);
 
 /* ---- binary index (replaces faiss.IndexBinaryFlat, fine_tune_ours.py:839-843,871-876) ------------ */
 
@@ -130,12 +155,16 @@ int sss_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits_in, 
 /* ---- item vote (replaces get_prediction_by_knn, test_amazon_filterd.py:59-78) -------------------- */
 
 /* For each of nq queries: neighbours I[q, 0..s) with weights D[q, 0..s); every item of neighbour
- * session j (items[item_off[j] .. item_off[j+1])) receives weight D[q, j]; weights are summed per item
- * in neighbour order; the top-K items by (weight desc, item id asc) are written to out_items [nq, K]
- * (-1 padded) and out_w [nq, K].  All buffers on the device. */
+ * session j (items[item_off[j] .. item_off[j+1])) receives weight D[q, j]; weights are summed per item in arrival
+ * order in float64 (the reference's defaultdict loop over a float64 array, :70-74); the top-K items by weight
+ * descending, equal weights in order of first arrival (Python's stable sort, :76), are written to out_items
+ * [nq, K] (-1 padded) and out_w [nq, K] (the float64 sums rounded to fp32).  All buffers on the device.
+ * max_votes: an upper bound on the votes of one query (s * longest item list) or 0 if unknown — it only sizes the
+ * shared-memory table.  Limits: K <= 256; item ids in [0, 2^32 - 2]; at most 12288 DISTINCT items voted for by one
+ * query (the number of votes is unbounded; the reference's own call, sample_size = 500 x <= 19 items, needs 9500). */
 int sss_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int64_t* item_off,
-                  const int64_t* items, int64_t n_sessions, int K, int64_t* out_items, float* out_w, int device,
-                  void* stream);
+                  const int64_t* items, int64_t n_sessions, int K, int64_t max_votes, int64_t* out_items,
+                  float* out_w, int device, void* stream);
 
 /* ---- session encoder (replaces UnifyPoolingGraphLevelEncoder.forward after the text embedder) ----- */
 
@@ -178,6 +207,23 @@ typedef struct sss_graph_batch {
  * input feature is NaN (the reference's isnan asserts, model/model.py:301-314, without host syncs). */
 int sss_encoder_forward(sss_encoder_t* enc, const sss_graph_batch_t* batch, float* out, int32_t* nonfinite,
                         void* stream);
+
+/* The two stages of the forward as the reference exposes them: gnn(x_dict, edge_index_dict) -> node embeddings
+ * (model/gnn.py:64-81) and pooling(node_emb_dict, data) -> [B, out_dim] (model/gnn.py:193-217), and the node
+ * embeddings of encoder(data, get_node=True) (model/model.py:344-351).
+ *   run_gnn = 1: HeteroGGNN over batch->x_query / x_product; the node embeddings [n, in_dim + n_layers * hidden]
+ *                (input features first, model/gnn.py:75-78) are written to z_query / z_product when non-NULL.
+ *   run_gnn = 0: z_query / z_product are INPUTS of the pooling stage (x_query / x_product and the edges are unused).
+ *   run_pooling = 1: PositionalAttentionPooling into out. */
+typedef struct sss_encoder_io {
+  float* out;
+  float* z_query;
+  float* z_product;
+  int run_gnn;
+  int run_pooling;
+  int32_t* nonfinite; /* as in sss_encoder_forward; may be NULL */
+} sss_encoder_io_t;
+int sss_encoder_forward_ex(sss_encoder_t* enc, const sss_graph_batch_t* batch, const sss_encoder_io_t* io, void* stream);
 
 /* Arithmetic of the encoder's dense linears.  SSS_ENCODER_MATH_FP32 (default): cuBLAS sgemm, pedantic fp32 on the
  * CUDA cores.  SSS_ENCODER_MATH_BF16X9: cuBLAS' fp32 emulation on the bf16 tensor cores (each operand split into
@@ -239,6 +285,48 @@ int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, ss
  * x [n, in], W [out, in], b [out], out [n, out]; device pointers. */
 int sss_binarize_head(const float* x, const float* W, const float* b, int64_t n, int in_dim, int out_dim,
                       float* out, int device, void* stream);
+
+/* ---- text-embedder tail (model/NodeEmbedding.py:112-125) ------------------------------------------------ */
+
+/* Masked mean over tokens: out[n, :] = sum_t tok[n, t, :] * mask[n, t] / sum_t mask[n, t] — what
+ * PretrainedQAEAEncoder.__call__ applies to the transformer's last_hidden_state.  tok fp32 [n, L, H], mask int64
+ * [n, L] (the tokenizer's attention_mask), out fp32 [n, H]; device pointers.  A row whose mask is all zero gives NaN,
+ * like the reference's 0 / 0. */
+int sss_masked_mean(const float* tok, const int64_t* mask, int64_t n, int L, int H, float* out, int device, void* stream);
+
+/* ---- in-batch cosine matrix (fine_tune_ours.py:133,480,494,613,626) ------------------------------------ */
+
+/* out[i, j] = <a_i / max(||a_i||, 1e-12), b_j / max(||b_j||, 1e-12)>  (F.normalize(a) @ F.normalize(b).T);
+ * a fp32 [na, d], b fp32 [nb, d], out fp32 [na, nb]; device pointers; fixed-order fp32 FMA. */
+int sss_cosine_matrix(const float* a, int64_t na, const float* b, int64_t nb, int d, float* out, int device,
+                      void* stream);
+
+/* ---- evaluation metrics on the retrieved ids (get_score / get_ave_score, fine_tune_ours.py:42-97,883-897) ---- */
+
+/* Ragged int64 lists per session in CSR form (device pointers): side a = the nq query sessions, side b = the database
+ * sessions; I int64 [nq, k] = retrieved ids; out fp32 [nq, k] = the reference's `gt` matrix (ids outside [0, n_b): 0).
+ * SSS_SCORE_JACCARD: lists hold each session's DISTINCT item ids (get_item: a set) -> |A & B| / |A | B|, 0 when both
+ *   are empty ('all_jaccard' over prefix + suffix, 'cur_jaccard' over the prefix only: the caller picks the lists).
+ * SSS_SCORE_TYPE_COSINE: lists hold the product-type ids of the item events in session order (get_item_type) ->
+ *   cosine of the count vectors in float64 with numpy's summation order ('all_product_type_score'); at most 64
+ *   distinct types per pair. */
+enum { SSS_SCORE_JACCARD = 0, SSS_SCORE_TYPE_COSINE = 1 };
+int sss_pair_scores(int kind, const int64_t* a_off, const int64_t* a_vals, int64_t nq, const int64_t* b_off,
+                    const int64_t* b_vals, int64_t n_b, const int64_t* I, int k, float* out, int device, void* stream);
+
+/* Lists of strings per session (HOST memory): strings seq_off[i] .. seq_off[i+1] belong to session i, string t is
+ * the UTF-32 code points chars[str_off[t] .. str_off[t+1]). */
+typedef struct sss_string_seqs {
+  int64_t n_seqs;
+  const int64_t* seq_off;
+  const int64_t* str_off;
+  const uint32_t* chars;
+} sss_string_seqs_t;
+/* out[q, j] = Levenshtein.seqratio(a[q], b[I[q, j]]) ('all_product_title_score'; with zero_if_empty = 1 the
+ * 'all_query_score' rule: 0 when either list is empty).  Native host code on n_threads threads (<= 0: all):
+ * string-sequence edit distance is nested dynamic programming over code points, not GPU work. */
+int sss_seqratio_pairs(const sss_string_seqs_t* a, const sss_string_seqs_t* b, const int64_t* I, int64_t nq, int k,
+                       int zero_if_empty, float* out, int n_threads);
 
 #ifdef __cplusplus
 }

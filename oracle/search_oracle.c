@@ -223,11 +223,14 @@ void o_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits) {
 
 /*
  * get_prediction_by_knn (test_amazon_filterd.py:59-78): item weight = sum over neighbour sessions (in
- * neighbour order) of that neighbour's similarity; top-K by (weight desc, item id asc).
+ * arrival order, accumulated in float64: `np.ones_like(int64 ids) * np.float32` is a float64 array, :71) of that
+ * neighbour's similarity; top-K by weight descending with Python's STABLE sort (:76), i.e. equal weights keep
+ * the order in which the items first arrived in the defaultdict (:72-74).  Pinned by tests/golden/vote_golden.npz,
+ * which the reference's own function produced.
  */
 typedef struct {
   int64_t item;
-  float w;
+  double w;
   int64_t first;
 } vote_t;
 static int cmp_item(const void* a, const void* b) {
@@ -239,7 +242,7 @@ static int cmp_item(const void* a, const void* b) {
 static int cmp_vote(const void* a, const void* b) {
   const vote_t *x = (const vote_t*)a, *y = (const vote_t*)b;
   if (x->w != y->w) return x->w > y->w ? -1 : 1;
-  return x->item < y->item ? -1 : (x->item > y->item ? 1 : 0);
+  return x->first < y->first ? -1 : (x->first > y->first ? 1 : 0);
 }
 int o_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int64_t* item_off, const int64_t* items,
                 int K, int64_t* out_items, float* out_w) {
@@ -265,9 +268,10 @@ int o_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int64
     int64_t u = 0;
     for (int64_t a = 0; a < m;) {
       int64_t b = a;
-      float w = 0.0f;
-      while (b < m && v[b].item == v[a].item) w += v[b++].w; /* neighbour order */
+      double w = 0.0;
+      while (b < m && v[b].item == v[a].item) w += v[b++].w; /* arrival order, float64 */
       v[u].item = v[a].item;
+      v[u].first = v[a].first;                               /* (a is the run head: the smallest arrival index) */
       v[u].w = w;
       ++u;
       a = b;
@@ -275,7 +279,7 @@ int o_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int64
     qsort(v, (size_t)u, sizeof(vote_t), cmp_vote);
     for (int j = 0; j < K; ++j) {
       out_items[qi * K + j] = j < u ? v[j].item : -1;
-      out_w[qi * K + j] = j < u ? v[j].w : 0.0f;
+      out_w[qi * K + j] = j < u ? (float)v[j].w : 0.0f;
     }
     free(v);
   }

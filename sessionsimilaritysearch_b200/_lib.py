@@ -29,6 +29,15 @@ class GraphBatch(ctypes.Structure):
                 ("e_pp", c_i64), ("pp_src", c_vp), ("pp_dst", c_vp)]
 
 
+class EncoderIO(ctypes.Structure):
+    _fields_ = [("out", c_vp), ("z_query", c_vp), ("z_product", c_vp), ("run_gnn", c_int), ("run_pooling", c_int),
+                ("nonfinite", c_vp)]
+
+
+class StringSeqs(ctypes.Structure):
+    _fields_ = [("n_seqs", c_i64), ("seq_off", c_vp), ("str_off", c_vp), ("chars", c_vp)]
+
+
 class FlatSessions(ctypes.Structure):
     _fields_ = [("n_sessions", c_i64), ("act_off", c_vp), ("act_is_search", c_vp), ("act_key", c_vp),
                 ("uniq_off", c_vp), ("uniq_items", c_vp)]
@@ -51,10 +60,13 @@ SIGNATURES = {
     "sss_index_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_int, c_int, c_i64]),
     "sss_index_destroy": (c_int, [c_vp]),
     "sss_index_add": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
-    "sss_index_set_segments": (c_int, [c_vp, c_vp, c_i64, c_int]),
+    "sss_index_set_segments": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "sss_index_ntotal": (c_i64, [c_vp]),
     "sss_index_dim": (c_int, [c_vp]),
     "sss_index_search": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "sss_packed_bytes": (c_i64, [c_i64, c_int]),
+    "sss_index_search_packed": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "sss_topk_merge_packed": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "sss_index_stat": (c_i64, [c_vp, c_int]),
     "sss_index_set_profiling": (c_int, [c_vp, c_int]),
     "sss_normalize": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
@@ -65,11 +77,17 @@ SIGNATURES = {
     "sss_binary_ntotal": (c_i64, [c_vp]),
     "sss_binary_search": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "sss_pack_sign_bits": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
-    "sss_item_vote": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
+    "sss_item_vote": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp]),
     "sss_encoder_create": (c_int, [ctypes.POINTER(c_vp), c_int, ctypes.POINTER(EncoderShape)]),
     "sss_encoder_destroy": (c_int, [c_vp]),
     "sss_encoder_set_param": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_int, c_vp]),
     "sss_encoder_forward": (c_int, [c_vp, ctypes.POINTER(GraphBatch), c_vp, c_vp, c_vp]),
+    "sss_encoder_forward_ex": (c_int, [c_vp, ctypes.POINTER(GraphBatch), ctypes.POINTER(EncoderIO), c_vp]),
+    "sss_masked_mean": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp]),
+    "sss_cosine_matrix": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
+    "sss_pair_scores": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
+    "sss_seqratio_pairs": (c_int, [ctypes.POINTER(StringSeqs), ctypes.POINTER(StringSeqs), c_vp, c_i64, c_int, c_int,
+                                   c_vp, c_int]),
     "sss_gather_rows": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_int, c_vp]),
     "sss_featurize_sizes": (c_int, [ctypes.POINTER(FlatSessions), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),

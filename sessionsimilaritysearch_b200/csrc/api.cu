@@ -45,10 +45,11 @@ static void dev_free(T*& p) {
 struct Workspace {
   int64_t nq_pad = 0;
   int cap = 0, d = 0, d_pad = 0, k = 0;
-  float *thr = nullptr, *margin = nullptr, *qn2 = nullptr, *q_f32 = nullptr, *out_D = nullptr;
+  float *thr = nullptr, *margin = nullptr, *qn2 = nullptr, *q_f32 = nullptr, *q_keep = nullptr, *out_D = nullptr;
   uint32_t *cnt = nullptr, *nret = nullptr, *skip_list = nullptr, *skip_cnt = nullptr;
   uint64_t* cand = nullptr;
-  int* flags = nullptr;  // [0] overflow, [1] kernel watchdog
+  int* flags = nullptr;       // [0] overflow, [1] kernel watchdog
+  int* host_flags = nullptr;  // pinned copy of flags (the one status word a search reads back)
   void* q_bf16 = nullptr;
   int64_t* out_I = nullptr;
   HitRecord* rec = nullptr;
@@ -58,25 +59,34 @@ struct Workspace {
   size_t rec_entries = 0;
   int n_regions = 0;
   int64_t out_elems = 0;
+  uint64_t generation = 0;    // bumped whenever a buffer is reallocated (captured graphs hold raw pointers)
 
   int ensure(int64_t nq_pad_, int cap_, int d_, int d_pad_, int64_t out_elems_) {
     if (nq_pad_ > nq_pad || cap_ > cap || d_ != d || d_pad_ != d_pad) {
       release_query_side();
+      ++generation;
       nq_pad = std::max(nq_pad_, nq_pad);
       cap = std::max(cap_, cap);
       d = d_;
       d_pad = d_pad_;
       if (dev_alloc(&thr, nq_pad) || dev_alloc(&margin, nq_pad) || dev_alloc(&qn2, nq_pad) || dev_alloc(&cnt, nq_pad) ||
-          dev_alloc(&nret, nq_pad) || dev_alloc(&skip_list, nq_pad) || dev_alloc(&skip_cnt, 2) || dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d))
+          dev_alloc(&nret, nq_pad) || dev_alloc(&skip_list, nq_pad) || dev_alloc(&skip_cnt, 2) ||
+          dev_alloc(&cand, (size_t)nq_pad * cap) || dev_alloc(&q_f32, (size_t)nq_pad * d) ||
+          dev_alloc(&q_keep, (size_t)nq_pad * d))
         return 1;
       void* v = nullptr;
       SSS_CUDA_OK(cudaMalloc(&v, (size_t)nq_pad * d_pad * 2));
       q_bf16 = v;
     }
-    if (!flags && dev_alloc(&flags, 2)) return 1;
+    if (!flags) {
+      if (dev_alloc(&flags, 2)) return 1;
+      SSS_CUDA_OK(cudaHostAlloc((void**)&host_flags, 2 * sizeof(int), cudaHostAllocDefault));
+      ++generation;
+    }
     if (out_elems_ > out_elems) {
       dev_free(out_D);
       dev_free(out_I);
+      ++generation;
       out_elems = out_elems_;
       if (dev_alloc(&out_D, out_elems) || dev_alloc(&out_I, out_elems)) return 1;
     }
@@ -86,26 +96,41 @@ struct Workspace {
     size_t need = (size_t)n_regions_ * rec_cap;
     if (need > rec_entries) {
       dev_free(rec);
+      ++generation;
       rec_entries = need;
       if (dev_alloc(&rec, rec_entries)) return 1;
     }
     if (n_regions_ > n_regions) {
       dev_free(rec_cnt);
+      ++generation;
       n_regions = n_regions_;
       if (dev_alloc(&rec_cnt, n_regions)) return 1;
     }
     return 0;
   }
+  int ensure_cmax(size_t need) {
+    if (need > cmax_elems) {
+      dev_free(cmax);
+      ++generation;
+      cmax_elems = need;
+      if (dev_alloc(&cmax, need)) return 1;
+    }
+    return 0;
+  }
   void release_query_side() {
-    dev_free(thr); dev_free(margin); dev_free(qn2); dev_free(cnt); dev_free(nret); dev_free(skip_list); dev_free(skip_cnt); dev_free(cand); dev_free(q_f32);
+    dev_free(thr); dev_free(margin); dev_free(qn2); dev_free(cnt); dev_free(nret); dev_free(skip_list); dev_free(skip_cnt);
+    dev_free(cand); dev_free(q_f32); dev_free(q_keep);
     if (q_bf16) cudaFree(q_bf16);
     q_bf16 = nullptr;
   }
   void release() {
     release_query_side();
     dev_free(flags); dev_free(out_D); dev_free(out_I); dev_free(rec); dev_free(rec_cnt); dev_free(cmax);
+    if (host_flags) cudaFreeHost(host_flags);
+    host_flags = nullptr;
     cmax_elems = 0;
     nq_pad = 0; cap = 0; rec_entries = 0; n_regions = 0; out_elems = 0;
+    ++generation;
   }
   SelectState state() const {
     SelectState s;
@@ -121,12 +146,12 @@ struct Workspace {
 struct RowStore {
   float* f32 = nullptr;
   void* bf16 = nullptr;
-  unsigned int* maxnorm2 = nullptr;  // device [2]: bits of max ||row||^2 and of max ||row - bf16(row)||^2
+  unsigned int* maxnorm2 = nullptr;  // device [4]: bits of max ||row||^2, max ||row - bf16(row)||^2, max ||row||_4^4
   int64_t n = 0, cap_rows = 0;
   int ensure(int64_t rows, int d, int d_pad, bool want_bf16, cudaStream_t st) {
     if (!maxnorm2) {
-      if (dev_alloc(&maxnorm2, 2)) return 1;
-      SSS_CUDA_OK(cudaMemsetAsync(maxnorm2, 0, 2 * sizeof(unsigned int), st));
+      if (dev_alloc(&maxnorm2, 4)) return 1;
+      SSS_CUDA_OK(cudaMemsetAsync(maxnorm2, 0, 4 * sizeof(unsigned int), st));
     }
     if (rows <= cap_rows) return 0;
     int64_t new_cap = std::max<int64_t>(rows, cap_rows + cap_rows / 2);
@@ -160,6 +185,47 @@ struct RowStore {
 
 using namespace sss;
 
+// Environment knobs, read ONCE when a handle is created (tuning and A/B runs; production needs none of them).
+struct Tuning {
+  int growth10 = 0;      // SSS_WAVE_GROWTH: wave growth factor x10 after the bootstrap pass (0 = default)
+  int64_t first = 0;     // SSS_WAVE_FIRST: rows of the first wave (0 = default)
+  bool no_bootstrap = false, no_lazy = false, no_graph = false;
+  int variant = 0;       // SSS_SCAN_VARIANT: ss | ts | 2cta (0 = automatic)
+  static Tuning from_env() {
+    Tuning t;
+    if (const char* g = getenv("SSS_WAVE_GROWTH")) t.growth10 = (int)std::max<int64_t>(11, atoll(g));
+    if (const char* f = getenv("SSS_WAVE_FIRST")) t.first = std::max<int64_t>(512, atoll(f) / 512 * 512);
+    auto on = [](const char* n) { const char* v = getenv(n); return v && v[0] == '1'; };
+    t.no_bootstrap = on("SSS_NO_BOOTSTRAP");
+    t.no_lazy = on("SSS_NO_LAZY");
+    t.no_graph = on("SSS_NO_GRAPH");
+    if (const char* v = getenv("SSS_SCAN_VARIANT")) t.variant = v[0] == 's' ? 1 : v[0] == 't' ? 2 : v[0] == '2' ? 3 : 0;
+    return t;
+  }
+};
+
+// One captured search: every launch from query staging to emit as a CUDA graph.  A step of the headline workload is
+// ~20 dependent kernels of 3-800 us; replayed as a graph they cost one host call and the launch gaps shrink to the
+// hardware's node-to-node latency.  Only two pointers differ between calls — the caller's query buffer (read by
+// prep_queries_kernel alone) and the output buffers (written by emit_kernel alone) — and those two kernel nodes are
+// re-bound with cudaGraphExecKernelNodeSetParams before every replay.
+struct SearchGraph {
+  int64_t nq = 0;
+  int k = 0, mode = 0;
+  uint64_t epoch = 0, ws_gen = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t prep = nullptr, emit = nullptr;
+  int64_t kernels = 0, waves = 0, variant = 0;
+  uint64_t last_use = 0;
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+  }
+};
+
 struct sss_index {
   int device = 0, d = 0, d_pad = 0, metric = 0, num_sms = 148;
   int64_t id_offset = 0;
@@ -173,22 +239,28 @@ struct sss_index {
   int64_t* seg_off = nullptr;  // device
   int32_t* row_seg = nullptr;  // device
   Workspace ws;
-  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0, stat_overflow_reason = 0, stat_variant = 0;
-  // optional scan-kernel timing (CUDA events on the launching stream around every scan launch)
+  Tuning tune;
+  uint64_t epoch = 1;          // bumped by add / set_segments / rec_boost changes: invalidates captured graphs
+  std::vector<SearchGraph> graphs;
+  uint64_t graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
+  int64_t stat_kernels = 0, stat_waves = 0, stat_reruns = 0, stat_overflow_reason = 0, stat_variant = 0, stat_graph = 0;
+  // optional scan-kernel timing (CUDA events on the launching stream around every scan launch; eager launches)
   bool profile = false;
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   double scan_us = 0.0;
   int64_t scan_launches = 0;
-  // refine of wave w runs on a side stream while the tensor-core scan of wave w+1 is already running
-  unsigned long long* dbg = nullptr;  // device [4], see RefineArgs::debug
+  unsigned long long* dbg = nullptr;  // device [12], see RefineArgs::debug
   unsigned long long dbg_host[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_ref[2] = {nullptr, nullptr};
+  void drop_graphs() {
+    for (auto& g : graphs) g.destroy();
+    graphs.clear();
+  }
 };
 
 extern "C" const char* sss_last_error(void) { return g_err.c_str(); }
-extern "C" int sss_version(void) { return 100; }
+extern "C" int sss_version(void) { return 200; }
 extern "C" int sss_built_for_sm(void) { return 100; }
 
 extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric, int64_t id_offset) {
@@ -211,6 +283,7 @@ extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric
   ix->id_offset = id_offset;
   ix->num_sms = prop.multiProcessorCount;
   ix->tensor_ok = ix->d_pad <= 4096;
+  ix->tune = Tuning::from_env();
   *out = ix;
   return 0;
 }
@@ -218,20 +291,20 @@ extern "C" int sss_index_create(sss_index_t** out, int device, int d, int metric
 extern "C" int sss_index_destroy(sss_index_t* ix) {
   if (!ix) return 0;
   DeviceGuard g(ix->device);
-  ix->rows.release();
-  ix->sums.release();
-  dev_free(ix->seg_off);
-  dev_free(ix->row_seg);
-  dev_free(ix->dbg);
-  ix->ws.release();
-  for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i) {
-    if (ix->ev_scan[i]) cudaEventDestroy(ix->ev_scan[i]);
-    if (ix->ev_ref[i]) cudaEventDestroy(ix->ev_ref[i]);
+  if (g.ok) {
+    cudaDeviceSynchronize();  // nothing of this handle may still be in flight when its buffers go
+    ix->drop_graphs();
+    ix->rows.release();
+    ix->sums.release();
+    dev_free(ix->seg_off);
+    dev_free(ix->row_seg);
+    dev_free(ix->dbg);
+    ix->ws.release();
+    for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+    if (ix->cap_stream) cudaStreamDestroy(ix->cap_stream);
   }
-  if (ix->side) cudaStreamDestroy(ix->side);
   delete ix;
-  return 0;
+  return g.ok ? 0 : 1;
 }
 
 extern "C" int64_t sss_index_ntotal(const sss_index_t* ix) { return ix ? ix->rows.n : 0; }
@@ -242,22 +315,19 @@ extern "C" int64_t sss_index_stat(const sss_index_t* ix, int what) {
     case 0: return ix->stat_kernels;
     case 1: return ix->stat_waves;
     case 2: return ix->stat_reruns;
-    case 24: return ix->stat_overflow_reason;
-    case 25: return ix->stat_variant;  // scan of the last search: 0 fp32, 1 SS, 2 TS, 3 pair (2-CTA), 4 K-loop pair  // bit mask of what overflowed in the last rerun (select.cu)
     case 3: return (int64_t)(ix->scan_us * 1000.0);  // scan-kernel time of the last search, ns (profiling on)
     case 4: return ix->scan_launches;
     case 5: return (int64_t)ix->dbg_host[0];  // candidates entering refine (profiling on)
     case 6: return (int64_t)ix->dbg_host[1];  // rows re-scored
     case 7: return (int64_t)ix->dbg_host[2];  // sessions sorted
     case 8: return (int64_t)ix->dbg_host[3];  // refine invocations (queries x waves with new candidates)
+#ifdef SSS_EXPERIMENT
     case 9: case 10: case 11: case 12: case 13: case 14: case 15:
       return (int64_t)ix->dbg_host[4 + (what - 9)];  // cycles of refine phase (what - 9), summed over invocations
-    case 16: case 17: case 18: case 19: case 20: case 21: case 22: case 23: {  // scan role wait cycles (SSS_SCAN_PROF experiments)
-      unsigned long long h[8] = {0};
-      if (!scan_prof_buffer()) return -1;
-      cudaMemcpy(h, scan_prof_buffer(), sizeof(h), cudaMemcpyDeviceToHost);
-      return (int64_t)h[what - 16];
-    }
+#endif
+    case 24: return ix->stat_overflow_reason;  // bit mask of what overflowed in the last rerun (select.cu)
+    case 25: return ix->stat_variant;  // scan of the last search: 0 fp32, 1 SS, 2 TS, 3 pair (2-CTA), 4 K-loop pair
+    case 26: return ix->stat_graph;    // 1 when the last search replayed a captured CUDA graph
     default: return -1;
   }
 }
@@ -278,12 +348,18 @@ extern "C" int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int 
   DeviceGuard g(ix->device);
   SSS_REQUIRE(g.ok, "sss_index_add: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
+  ix->epoch += 1;
+  ix->drop_graphs();
   if (ix->rows.ensure(ix->rows.n + n, ix->d, ix->d_pad, ix->tensor_ok, st)) return 1;
   const float* src = rows;
   float* staged = nullptr;
   if (!rows_on_device) {
     if (dev_alloc(&staged, (size_t)n * ix->d)) return 1;
-    SSS_CUDA_OK(cudaMemcpyAsync(staged, rows, (size_t)n * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (cudaMemcpyAsync(staged, rows, (size_t)n * ix->d * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      cudaFree(staged);
+      set_error("sss_index_add: host to device copy failed");
+      return 1;
+    }
     src = staged;
   }
   int rc = launch_add_rows(src, n, ix->d, ix->d_pad, norm_mode, ix->rows.f32, ix->rows.bf16, ix->rows.n,
@@ -299,44 +375,68 @@ extern "C" int sss_index_add(sss_index_t* ix, const float* rows, int64_t n, int 
   return 0;
 }
 
-extern "C" int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce) {
+// All of its work is enqueued on `stream` — the stream the rows were added on, or one ordered after it — and the call
+// returns after that stream has drained (the segment offsets are host memory and the summed rows are built here).
+extern "C" int sss_index_set_segments(sss_index_t* ix, const int64_t* seg_off, int64_t n_seg, int reduce, void* stream) {
   SSS_REQUIRE(ix != nullptr, "sss_index_set_segments: NULL index");
   SSS_REQUIRE(reduce >= 0 && reduce <= 2, "sss_index_set_segments: unknown reduce");
   DeviceGuard g(ix->device);
+  SSS_REQUIRE(g.ok, "sss_index_set_segments: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
   if (reduce == SSS_REDUCE_NONE) {
+    ix->epoch += 1;
+    ix->drop_graphs();
     ix->reduce = 0;
     ix->n_seg = 0;
     return 0;
   }
+  // validate everything before touching the index: a rejected call leaves it exactly as it was
   SSS_REQUIRE(seg_off != nullptr && n_seg >= 1, "sss_index_set_segments: need seg_off[n_seg+1]");
   SSS_REQUIRE(seg_off[0] == 0 && seg_off[n_seg] == ix->rows.n, "sss_index_set_segments: seg_off must span [0, ntotal]");
+  SSS_REQUIRE(reduce != SSS_REDUCE_SUM || ix->metric == SSS_METRIC_IP,
+              "reduce = sum is defined for the inner-product metric only (a sum of distances is not a distance to a sum)");
   int64_t max_len = 1;
   for (int64_t s = 0; s < n_seg; ++s) {
     SSS_REQUIRE(seg_off[s + 1] >= seg_off[s], "sss_index_set_segments: seg_off must be non-decreasing");
     max_len = std::max(max_len, seg_off[s + 1] - seg_off[s]);
   }
-  ix->max_seg_len = max_len;
+  int64_t* new_off = nullptr;
+  int32_t* new_map = nullptr;
+  float* tmp = nullptr;
+  RowStore new_sums;
+  int rc = dev_alloc(&new_off, n_seg + 1) || dev_alloc(&new_map, ix->rows.n);
+  if (!rc && cudaMemcpyAsync(new_off, seg_off, (size_t)(n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_error("sss_index_set_segments: host to device copy failed");
+    rc = 1;
+  }
+  if (!rc) rc = launch_row_seg(new_off, n_seg, new_map, st);
+  if (!rc && reduce == SSS_REDUCE_SUM) {
+    // linearity: sum_r <q, x_r> = <q, sum_r x_r>; build the summed rows once, then search them as rows
+    rc = new_sums.ensure(n_seg, ix->d, ix->d_pad, ix->tensor_ok, st) || dev_alloc(&tmp, (size_t)n_seg * ix->d);
+    if (!rc) rc = launch_segment_sum(ix->rows.f32, new_off, n_seg, ix->d, tmp, st);
+    if (!rc) rc = launch_add_rows(tmp, n_seg, ix->d, ix->d_pad, 0, new_sums.f32, new_sums.bf16, 0, new_sums.maxnorm2, st);
+    if (!rc) new_sums.n = n_seg;
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess && !rc) {
+    set_error("sss_index_set_segments: CUDA failure while building the segment map");
+    rc = 1;
+  }
+  dev_free(tmp);
+  if (rc) {
+    dev_free(new_off);
+    dev_free(new_map);
+    new_sums.release();
+    return 1;
+  }
+  ix->epoch += 1;
+  ix->drop_graphs();
   dev_free(ix->seg_off);
   dev_free(ix->row_seg);
-  if (dev_alloc(&ix->seg_off, n_seg + 1) || dev_alloc(&ix->row_seg, ix->rows.n)) return 1;
-  SSS_CUDA_OK(cudaMemcpy(ix->seg_off, seg_off, (size_t)(n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-  if (launch_row_seg(ix->seg_off, n_seg, ix->row_seg, 0)) return 1;
-  SSS_REQUIRE(reduce != SSS_REDUCE_SUM || ix->metric == SSS_METRIC_IP,
-              "reduce = sum is defined for the inner-product metric only (a sum of distances is not a distance to a sum)");
-  if (reduce == SSS_REDUCE_SUM) {
-    // linearity: sum_r <q, x_r> = <q, sum_r x_r>; build the summed rows once, then search them as rows
-    ix->sums.release();
-    if (ix->sums.ensure(n_seg, ix->d, ix->d_pad, ix->tensor_ok, 0)) return 1;
-    float* tmp = nullptr;
-    if (dev_alloc(&tmp, (size_t)n_seg * ix->d)) return 1;
-    int rc = launch_segment_sum(ix->rows.f32, ix->seg_off, n_seg, ix->d, tmp, 0);
-    if (!rc) rc = launch_add_rows(tmp, n_seg, ix->d, ix->d_pad, 0, ix->sums.f32, ix->sums.bf16, 0, ix->sums.maxnorm2, 0);
-    cudaStreamSynchronize(0);
-    cudaFree(tmp);
-    if (rc) return rc;
-    ix->sums.n = n_seg;
-  }
-  SSS_CUDA_OK(cudaStreamSynchronize(0));
+  ix->sums.release();
+  ix->seg_off = new_off;
+  ix->row_seg = new_map;
+  ix->sums = new_sums;
+  ix->max_seg_len = max_len;
   ix->reduce = reduce;
   ix->n_seg = n_seg;
   return 0;
@@ -346,18 +446,15 @@ namespace sss {
 
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
-static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups = false,
-                                       int64_t bootstrap_rows = 0, bool few_queries = false) {
+static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups,
+                                       int64_t bootstrap_rows, const Tuning& tune) {
   std::vector<int64_t> ends;
   if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): re-scan those rows first
-    // Measured at 10M rows x 1000 queries (profiles/r01_wave_schedule.md): refine cost follows the candidate volume,
-    // not the wave count, so longer waves buy nothing there, and from x3.5 on a (query, pair, warpgroup) record
-    // sub-region can exceed its 16 records.  With a single m-tile the launch count dominates and the 1-CTA scan has
-    // twice the sub-regions per query: x3.
-    const char* g = getenv("SSS_WAVE_GROWTH");  // tuning: growth factor x10
-    const char* f = getenv("SSS_WAVE_FIRST");   // tuning: rows of the first wave
-    const int64_t growth10 = g ? std::max<int64_t>(11, atoll(g)) : (few_queries ? 30 : 20);
-    int64_t e = f ? std::max<int64_t>(512, atoll(f) / 512 * 512) : bootstrap_rows;
+    // Between waves the lazy refine costs ~30 us per wave almost independently of the candidate volume
+    // (profiles/r02_wave_growth.md: 10M rows x 1000 queries, x2 / 8 waves 2.46 ms, x3 / 5 waves 2.39 ms, x4 2.56 ms:
+    // above x3 the record sub-regions of a (query, pair, warpgroup) start to overflow their 16 records).
+    const int64_t growth10 = tune.growth10 ? tune.growth10 : 30;
+    int64_t e = tune.first ? tune.first : bootstrap_rows;
     e = std::min(e, n_rows);
     ends.push_back(e);
     while (e < n_rows) {
@@ -395,24 +492,223 @@ struct BatchArgs {
   int64_t* I;
 };
 
+// Everything a search pass needs that does not depend on the attempt: operands, plan, tensor maps.
+struct SearchCtx {
+  RowStore* rs = nullptr;
+  int64_t n_rows = 0, nq = 0, nq_pad = 0;
+  int k = 0, mode = 0, cap = 4096;
+  bool tensor = false, l2_tensor = false, rescoring = false;
+  Bf16ScanPlan plan{};
+  alignas(64) unsigned char tmap_q[128];
+  alignas(64) unsigned char tmap_db[128];
+  int64_t kernels = 0, waves = 0;  // filled by enqueue_search
+};
+
+static int replan(sss_index* ix, SearchCtx& c) {
+  if (!c.tensor) return 0;
+  if (plan_scan_bf16(ix->d_pad, c.nq_pad, ix->num_sms, 8, &c.plan, ix->rec_boost,
+                     ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0), ix->tune.variant))
+    return 1;
+  return ix->ws.ensure_records(2 * c.plan.n_regions, c.plan.rec_cap);
+}
+
+// Enqueue one whole search on `st`: query staging, bootstrap thresholds, scan + refine waves, emit.  No allocation and
+// no synchronisation in here (it is what gets captured into a graph); `profile` adds CUDA events around the scans.
+static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev, bool safe,
+                          bool profile, cudaStream_t st) {
+  Workspace& ws = ix->ws;
+  RowStore& rs = *c.rs;
+  const int64_t n_rows = c.n_rows;
+  const bool tensor = c.tensor;
+  const Bf16ScanPlan& plan = c.plan;
+  c.kernels = c.waves = 0;
+  SelectState state = ws.state();
+  state.cap = c.cap;
+  const int slack = !tensor ? 0 : c.mode == SSS_MODE_EXACT ? 1 : 2;
+  if (launch_prep_queries(q_in, c.nq, c.nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr, slack, rs.maxnorm2, state,
+                          st, c.l2_tensor ? 1 : 0, ws.q_keep))
+    return 1;
+  SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
+  c.kernels += 1;
+  RefineArgs ra;
+  ra.nq = c.nq;
+  ra.k = c.k;
+  ra.reduce_max = ix->reduce == SSS_REDUCE_MAX;
+  ra.row_seg = ix->row_seg;
+  ra.db_f32 = rs.f32;
+  ra.q_f32 = ws.q_keep;
+  ra.d = ix->d;
+  ra.metric = ix->metric;
+  ra.debug = nullptr;
+  if (profile && ix->dbg) {
+    SSS_CUDA_OK(cudaMemsetAsync(ix->dbg, 0, 12 * sizeof(unsigned long long), st));
+    ra.debug = ix->dbg;
+  }
+  // Bootstrap: one tensor-core pass in chunk-max mode over the first rows (128K; for smaller indexes the largest
+  // power of two within half of the rows) gives every query a valid threshold at once and replaces the short first
+  // waves (and, with re-scoring, the fp32 first wave and the per-wave re-scoring: lazy mode needs tensor waves only).
+  int64_t boot_rows = 131072;
+  while (boot_rows > 4096 && boot_rows * 2 > n_rows) boot_rows >>= 1;
+  const int n_boot_chunks = (int)(boot_rows / 32);
+  const bool grouped = ix->reduce == SSS_REDUCE_MAX;
+  const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
+  const bool bootstrap = tensor && (plan.ts || plan.two_cta || plan.kloop) && !safe && n_rows >= 2 * boot_rows &&
+                         !ix->tune.no_bootstrap && (int64_t)(c.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4 &&
+                         ws.cmax_elems >= (size_t)n_boot_chunks * (size_t)c.nq_pad;
+  if (bootstrap) {
+    if (launch_scan_bf16(plan, c.tmap_q, c.tmap_db, ws.q_bf16, 0, boot_rows, state, ws.rec, ws.rec_cnt, ws.flags + 1,
+                         ws.cmax, st))
+      return 1;
+    if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, c.nq, c.nq_pad, c.k, chunk_gap, 2.0f, state, st)) return 1;
+    c.kernels += 2;
+  }
+  const std::vector<int64_t> ends = make_waves(n_rows, c.cap, c.k, safe, grouped, bootstrap ? boot_rows : 0, ix->tune);
+  int64_t begin = 0;
+  uint32_t wave_id = 0;
+  for (int64_t end : ends) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+      while (ix->ev.size() < ix->ev_used + 2) {
+        cudaEvent_t e;
+        SSS_CUDA_OK(cudaEventCreate(&e));
+        ix->ev.push_back(e);
+      }
+      e0 = ix->ev[ix->ev_used++];
+      e1 = ix->ev[ix->ev_used++];
+    }
+    // The first wave has no threshold: every score is a candidate.  With re-scoring it is cheaper to get those
+    // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
+    const bool wave_tensor = tensor && !(c.rescoring && begin == 0 && !bootstrap);
+    const uint32_t w = ++wave_id;
+    const int buf = (int)(w & 1u);
+    HitRecord* rec_buf = ws.rec + (tensor ? (size_t)buf * plan.n_regions * plan.rec_cap : 0);
+    uint32_t* cnt_buf = ws.rec_cnt + (tensor ? (size_t)buf * plan.n_regions : 0);
+    ra.rescore = c.rescoring && wave_tensor;
+    ra.wave = w;
+    ra.rec = wave_tensor ? rec_buf : nullptr;
+    ra.rec_cnt = cnt_buf;
+    ra.rec_nsub = tensor ? plan.rec_nsub : 0;
+    ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
+    ra.l2_tensor = c.l2_tensor ? 1 : 0;
+    ra.lazy = (c.rescoring && !safe && c.k <= 256 && !ix->tune.no_lazy) ? 1 : 0;
+    ra.final = end == ends.back() ? 1 : 0;
+    ra.row_limit = n_rows;
+    if (e0) SSS_CUDA_OK(cudaEventRecord(e0, st));
+    if (wave_tensor) {
+      if (launch_scan_bf16(plan, c.tmap_q, c.tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1,
+                           nullptr, st))
+        return 1;
+    } else {
+      if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, ws.q_keep, c.nq, state, st)) return 1;
+    }
+    if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
+    if (launch_refine(ra, state, ix->num_sms, st)) return 1;
+    c.kernels += 1 + (c.k <= 256 ? 2 : 1);
+    c.waves += 1;
+    begin = end;
+  }
+  if (launch_emit(state, c.nq, c.k, ix->metric, ix->id_offset, Ddev, Idev, st)) return 1;
+  c.kernels += 1;
+  return 0;
+}
+
+static int find_graph_nodes(SearchGraph& g) {
+  size_t n = 0;
+  SSS_CUDA_OK(cudaGraphGetNodes(g.graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  SSS_CUDA_OK(cudaGraphGetNodes(g.graph, nodes.data(), &n));
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    SSS_CUDA_OK(cudaGraphNodeGetType(nodes[i], &t));
+    if (t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    SSS_CUDA_OK(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+    if (kp.func == prep_queries_kernel_addr()) g.prep = nodes[i];
+    if (kp.func == emit_kernel_addr()) g.emit = nodes[i];
+  }
+  SSS_REQUIRE(g.prep != nullptr && g.emit != nullptr, "captured search graph lacks its staging / emit nodes");
+  return 0;
+}
+
+// re-bind pointer arguments of one kernel node: (argument index, new value) pairs
+static int rebind(SearchGraph& g, cudaGraphNode_t node, int n_args, int i0, const void* v0, int i1 = -1,
+                  const void* v1 = nullptr) {
+  cudaKernelNodeParams kp;
+  SSS_CUDA_OK(cudaGraphKernelNodeGetParams(node, &kp));
+  SSS_REQUIRE(kp.kernelParams != nullptr && n_args <= 16, "captured kernel node exposes no parameter array");
+  void* args[16];
+  for (int i = 0; i < n_args; ++i) args[i] = kp.kernelParams[i];
+  args[i0] = (void*)&v0;
+  if (i1 >= 0) args[i1] = (void*)&v1;
+  kp.kernelParams = args;
+  kp.extra = nullptr;
+  SSS_CUDA_OK(cudaGraphExecKernelNodeSetParams(g.exec, node, &kp));
+  return 0;
+}
+
+static SearchGraph* capture_graph(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev) {
+  if (!ix->cap_stream && cudaStreamCreateWithFlags(&ix->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  SearchGraph g;
+  g.nq = c.nq;
+  g.k = c.k;
+  g.mode = c.mode;
+  g.epoch = ix->epoch;
+  g.ws_gen = ix->ws.generation;
+  if (cudaStreamBeginCapture(ix->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  const int rc = enqueue_search(ix, c, q_in, Ddev, Idev, false, false, ix->cap_stream);
+  cudaError_t e = cudaStreamEndCapture(ix->cap_stream, &g.graph);
+  if (rc != 0 || e != cudaSuccess || g.graph == nullptr) {
+    cudaGetLastError();
+    g.destroy();
+    return nullptr;
+  }
+  if (cudaGraphInstantiate(&g.exec, g.graph, 0) != cudaSuccess || find_graph_nodes(g)) {
+    cudaGetLastError();
+    g.destroy();
+    return nullptr;
+  }
+  g.kernels = c.kernels;
+  g.waves = c.waves;
+  if (ix->graphs.size() >= 6) {  // a handful of (nq, k, mode) shapes per index: drop the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < ix->graphs.size(); ++i)
+      if (ix->graphs[i].last_use < ix->graphs[lru].last_use) lru = i;
+    ix->graphs[lru].destroy();
+    ix->graphs.erase(ix->graphs.begin() + lru);
+  }
+  ix->graphs.push_back(g);
+  return &ix->graphs.back();
+}
+
 static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   const bool use_sums = ix->reduce == SSS_REDUCE_SUM;
-  RowStore& rs = use_sums ? ix->sums : ix->rows;
-  const int64_t n_rows = rs.n;
-  int mode = b.mode;
-  if (mode != SSS_MODE_FP32 && !ix->tensor_ok) {
-    SSS_REQUIRE(mode == SSS_MODE_EXACT,
-                "SSS_MODE_BF16 needs d <= 4096 (d <= 4095 for L2); use SSS_MODE_EXACT or SSS_MODE_FP32");
-    mode = SSS_MODE_FP32;  // EXACT is defined as "bit-identical to FP32": run the fp32 scan itself
-  }
-  const bool tensor = mode != SSS_MODE_FP32 && n_rows > 0;
-  const bool l2_tensor = tensor && ix->metric == SSS_METRIC_L2;
+  SearchCtx c;
+  c.rs = use_sums ? &ix->sums : &ix->rows;
+  c.n_rows = c.rs->n;
+  c.nq = b.nq;
+  c.k = b.k;
+  c.mode = b.mode;
+  if (c.mode != SSS_MODE_FP32 && !ix->tensor_ok) c.mode = SSS_MODE_FP32;  // no tensor path for d_pad > 4096: the fp32 scan IS the exact result
+  c.tensor = c.mode != SSS_MODE_FP32 && c.n_rows > 0;
+  c.l2_tensor = c.tensor && ix->metric == SSS_METRIC_L2;
+  c.rescoring = c.mode != SSS_MODE_FP32;
   ix->stat_variant = 0;
-  const int cap = 4096;
-  SSS_REQUIRE(b.k <= cap / 2, "k too large (max 2048)");
-  const int64_t nq_pad = (b.nq + 127) / 128 * 128;
+  ix->stat_graph = 0;
+  SSS_REQUIRE(b.k <= c.cap / 2, "k too large (max 2048)");
+  c.nq_pad = (b.nq + 127) / 128 * 128;
   Workspace& ws = ix->ws;
-  if (ws.ensure(nq_pad, cap, ix->d, ix->d_pad, b.out_on_device ? 0 : b.nq * b.k)) return 1;
+  if (ws.ensure(c.nq_pad, c.cap, ix->d, ix->d_pad, b.out_on_device ? 0 : b.nq * b.k)) return 1;
+  if (replan(ix, c)) return 1;
+  if (c.tensor) {
+    ix->stat_variant = c.plan.kloop ? 4 : c.plan.two_cta ? 3 : c.plan.ts ? 2 : 1;
+    if (ws.ensure_cmax((size_t)4096 * (size_t)c.nq_pad)) return 1;
+    if (make_tensor_map_bf16_2d(c.tmap_q, ws.q_bf16, (uint64_t)c.nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
+    if (make_tensor_map_bf16_2d(c.tmap_db, c.rs->bf16, (uint64_t)c.n_rows, (uint64_t)ix->d_pad, 128)) return 1;
+  }
+  if (ix->profile && !ix->dbg && dev_alloc(&ix->dbg, 12)) return 1;
   const float* qdev = b.q;
   if (!b.q_on_device) {
     SSS_CUDA_OK(cudaMemcpyAsync(ws.q_f32, b.q, (size_t)b.nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -421,156 +717,36 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   float* Ddev = b.out_on_device ? b.D : ws.out_D;
   int64_t* Idev = b.out_on_device ? b.I : ws.out_I;
 
-  Bf16ScanPlan plan;
-  alignas(64) unsigned char tmap_q[128], tmap_db[128];
-  const char* ov = getenv("SSS_OVERLAP");  // experimental: refine(w) on a side stream under scan(w+1)
-  const bool overlap = tensor && ov && ov[0] == '1';
-  if (tensor) {
-    // leave shared memory for the refine blocks that co-run with the scan when overlapping
-    if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost,
-                       ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0))) return 1;
-    if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
-    ix->stat_variant = plan.kloop ? 4 : plan.two_cta ? 3 : plan.ts ? 2 : 1;
-    if (overlap && !ix->side) {
-      SSS_CUDA_OK(cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; ++i) {
-        SSS_CUDA_OK(cudaEventCreateWithFlags(&ix->ev_scan[i], cudaEventDisableTiming));
-        SSS_CUDA_OK(cudaEventCreateWithFlags(&ix->ev_ref[i], cudaEventDisableTiming));
-      }
-    }
-    if (make_tensor_map_bf16_2d(tmap_q, ws.q_bf16, (uint64_t)nq_pad, (uint64_t)ix->d_pad, 128)) return 1;
-    if (make_tensor_map_bf16_2d(tmap_db, rs.bf16, (uint64_t)n_rows, (uint64_t)ix->d_pad, 128)) return 1;
-  }
-  // Attempts: the normal schedule; if ONLY a record sub-region overflowed (a hot spot of one query inside one CTA's
-  // share of a wave), the same schedule again with 4x the records per sub-region (the index remembers that); anything
-  // else, or a second overflow, falls back to the safe schedule of 2048-row waves.
+  // Attempts: the normal schedule (replayed from a captured graph when there is one); if ONLY a record sub-region
+  // overflowed (a hot spot of one query inside one CTA's share of a wave), the same schedule again with 4x the records
+  // per sub-region (the index remembers that); anything else, or a second overflow, falls back to the safe schedule
+  // of 2048-row waves.
   bool safe = false;
   for (int attempt = 0; attempt < 3; ++attempt) {
-    if (tensor && plan.rec_cap != (plan.kloop ? 4 : 1) * kRecSubCap * ix->rec_boost) {
-      if (plan_scan_bf16(ix->d_pad, nq_pad, ix->num_sms, overlap ? 5 : 8, &plan, ix->rec_boost,
-                       ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0))) return 1;
-      if (ws.ensure_records(2 * plan.n_regions, plan.rec_cap)) return 1;
-    }
-    SelectState state = ws.state();
-    state.cap = cap;
-    if (launch_prep_queries(qdev, b.nq, nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr,
-                            mode == SSS_MODE_EXACT ? 1 : 0, rs.maxnorm2, state, st, l2_tensor ? 1 : 0))
-      return 1;
-    SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
-    ix->stat_kernels += 1;
-    RefineArgs ra;
-    ra.nq = b.nq;
-    ra.k = b.k;
-    ra.reduce_max = ix->reduce == SSS_REDUCE_MAX;
-    ra.row_seg = ix->row_seg;
-    ra.rescore = mode == SSS_MODE_EXACT;
-    ra.db_f32 = rs.f32;
-    ra.q_f32 = qdev;
-    ra.d = ix->d;
-    ra.metric = ix->metric;
-    ra.debug = nullptr;
-    if (ix->profile) {
-      if (!ix->dbg && dev_alloc(&ix->dbg, 12)) return 1;
-      SSS_CUDA_OK(cudaMemsetAsync(ix->dbg, 0, 12 * sizeof(unsigned long long), st));
-      ra.debug = ix->dbg;
-    }
-    // Bootstrap: one tensor-core pass in chunk-max mode over the first rows (128K; for smaller indexes the largest
-    // power of two within half of the rows) gives every query a valid threshold at once and replaces the short first
-    // waves (and, in EXACT mode, the fp32 first wave and the per-wave re-scoring: lazy mode needs tensor waves only).
-    int64_t kBootRows = 131072;
-    while (kBootRows > 4096 && kBootRows * 2 > n_rows) kBootRows >>= 1;
-    const int n_boot_chunks = (int)(kBootRows / 32);
-    const bool grouped = ix->reduce == SSS_REDUCE_MAX;
-    const int chunk_gap = grouped ? (int)((ix->max_seg_len + 30) / 32) + 1 : 1;
-    const char* no_boot = getenv("SSS_NO_BOOTSTRAP");
-    const bool bootstrap = tensor && (plan.ts || plan.two_cta || plan.kloop) && !safe && n_rows >= 2 * kBootRows && !(no_boot && no_boot[0] == '1') &&
-                           (int64_t)(b.k - 1) * chunk_gap + 1 <= n_boot_chunks / 4;
-    if (bootstrap) {
-      const size_t need = (size_t)n_boot_chunks * (size_t)nq_pad;
-      if (need > ws.cmax_elems) {
-        dev_free(ws.cmax);
-        ws.cmax_elems = need;
-        if (dev_alloc(&ws.cmax, need)) return 1;
-      }
-      if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, 0, kBootRows, state, ws.rec, ws.rec_cnt, ws.flags + 1,
-                           ws.cmax, st))
-        return 1;
-      if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, b.nq, nq_pad, b.k, chunk_gap, 2.0f, state, st)) return 1;
-      ix->stat_kernels += 2;
-    }
-    std::vector<int64_t> ends = make_waves(n_rows, cap, b.k, safe, grouped, bootstrap ? kBootRows : 0, tensor && plan.total_mtiles == 1);
-    int64_t begin = 0;
-    uint32_t wave_id = 0;
-    const char* nl_env = getenv("SSS_NO_LAZY");  // A/B switch: exact re-scoring in every wave
-    const bool no_lazy = nl_env && nl_env[0] == '1';
-    bool prev_tensor = false;
-    for (int64_t end : ends) {
-      cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (ix->profile) {
-        while (ix->ev.size() < ix->ev_used + 2) {
-          cudaEvent_t e;
-          SSS_CUDA_OK(cudaEventCreate(&e));
-          ix->ev.push_back(e);
-        }
-        e0 = ix->ev[ix->ev_used++];
-        e1 = ix->ev[ix->ev_used++];
-      }
-      // The first wave has no threshold: every score is a candidate.  In EXACT mode it is cheaper to get those
-      // scores exactly from the fp32 scan than to rescore all of them after a tensor-core pass.
-      const bool wave_tensor = tensor && !(mode == SSS_MODE_EXACT && begin == 0 && !bootstrap);
-      const uint32_t w = ++wave_id;
-      const int buf = (int)(w & 1u);
-      HitRecord* rec_buf = ws.rec + (tensor ? (size_t)buf * plan.n_regions * plan.rec_cap : 0);
-      uint32_t* cnt_buf = ws.rec_cnt + (tensor ? (size_t)buf * plan.n_regions : 0);
-      ra.rescore = mode == SSS_MODE_EXACT && wave_tensor;
-      ra.wave = w;
-      ra.rec = wave_tensor ? rec_buf : nullptr;
-      ra.rec_cnt = cnt_buf;
-      ra.rec_nsub = tensor ? plan.rec_nsub : 0;
-      ra.rec_cap = tensor ? plan.rec_cap : kRecSubCap;
-      ra.l2_tensor = l2_tensor ? 1 : 0;
-      ra.lazy = (mode == SSS_MODE_EXACT && !safe && b.k <= 256 && !no_lazy) ? 1 : 0;
-      ra.final = end == ends.back() ? 1 : 0;
-      ra.row_limit = n_rows;
-      // Long tensor-core waves do not wait for the refine of the wave before them: they start with the
-      // thresholds of two waves ago and pick up the newer ones as refine publishes them (thresholds only ever
-      // rise, and refine re-filters every record against the current threshold, so this is still exact).
-      const bool late = overlap && !safe && wave_tensor && prev_tensor && end - begin >= 524288;
-      if (overlap) {
-        if (w >= 3) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf], 0));                 // records[buf] are free
-        if (w >= 2 && !late) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[buf ^ 1], 0));    // fresh thresholds
-      }
-      if (e0) SSS_CUDA_OK(cudaEventRecord(e0, st));
-      if (wave_tensor) {
-        if (launch_scan_bf16(plan, tmap_q, tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1,
-                             nullptr, st))
-          return 1;
+    if (c.tensor && c.plan.rec_cap != (c.plan.kloop ? 4 : 1) * kRecSubCap * ix->rec_boost && replan(ix, c)) return 1;
+    bool launched = false;
+    if (!safe && !ix->profile && !ix->tune.no_graph) {
+      SearchGraph* g = nullptr;
+      for (auto& cand : ix->graphs)
+        if (cand.nq == c.nq && cand.k == c.k && cand.mode == c.mode && cand.epoch == ix->epoch &&
+            cand.ws_gen == ws.generation)
+          g = &cand;
+      if (!g) g = capture_graph(ix, c, qdev, Ddev, Idev);
+      if (g && rebind(*g, g->prep, 11, 0, qdev) == 0 && rebind(*g, g->emit, 7, 5, Ddev, 6, Idev) == 0 &&
+          cudaGraphLaunch(g->exec, st) == cudaSuccess) {
+        g->last_use = ++ix->graph_clock;
+        c.kernels = g->kernels;
+        c.waves = g->waves;
+        ix->stat_graph = 1;
+        launched = true;
       } else {
-        if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, qdev, b.nq, state, st)) return 1;
+        cudaGetLastError();  // graphs are an optimisation: anything unexpected falls back to plain launches
       }
-      if (e1) SSS_CUDA_OK(cudaEventRecord(e1, st));
-      ix->stat_kernels += 1;
-      if (overlap) {
-        SSS_CUDA_OK(cudaEventRecord(ix->ev_scan[buf], st));
-        SSS_CUDA_OK(cudaStreamWaitEvent(ix->side, ix->ev_scan[buf], 0));
-        if (launch_refine(ra, state, ix->num_sms, ix->side)) return 1;
-        SSS_CUDA_OK(cudaEventRecord(ix->ev_ref[buf], ix->side));
-      } else {
-        if (launch_refine(ra, state, ix->num_sms, st)) return 1;
-      }
-      ix->stat_kernels += b.k <= 256 ? 2 : 1;
-      ix->stat_waves += 1;
-      prev_tensor = wave_tensor;
-      begin = end;
     }
-    if (overlap && wave_id >= 1) {
-      SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[wave_id & 1u], 0));
-      if (wave_id >= 2) SSS_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_ref[(wave_id & 1u) ^ 1u], 0));
-    }
-    if (launch_emit(state, b.nq, b.k, ix->metric, ix->id_offset, Ddev, Idev, st)) return 1;
-    ix->stat_kernels += 1;
-    int flags[2] = {0, 0};
-    SSS_CUDA_OK(cudaMemcpyAsync(flags, ws.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, safe, ix->profile, st)) return 1;
+    ix->stat_kernels += c.kernels;
+    ix->stat_waves += c.waves;
+    SSS_CUDA_OK(cudaMemcpyAsync(ws.host_flags, ws.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!b.out_on_device) {
       SSS_CUDA_OK(cudaMemcpyAsync(b.D, Ddev, (size_t)b.nq * b.k * sizeof(float), cudaMemcpyDeviceToHost, st));
       SSS_CUDA_OK(cudaMemcpyAsync(b.I, Idev, (size_t)b.nq * b.k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -587,33 +763,35 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       }
       ix->ev_used = 0;
     }
-    SSS_REQUIRE(flags[1] == 0, "tensor-core scan watchdog fired (barrier code " + std::to_string(flags[1]) + ")");
-    if (flags[0] == 0) return 0;
+    const int f_over = ws.host_flags[0], f_dog = ws.host_flags[1];
+    SSS_REQUIRE(f_dog == 0, "tensor-core scan watchdog fired (barrier code " + std::to_string(f_dog) + ")");
+    if (f_over == 0) return 0;
     // a candidate list or record region overflowed (adversarial score order): redo with waves that
     // cannot overflow by construction
     SSS_REQUIRE(!safe, "candidate overflow persisted in the safe wave schedule (internal error)");
     ix->stat_reruns += 1;
-    ix->stat_overflow_reason = flags[0];
-    if (tensor && flags[0] == 1 && ix->rec_boost == 1)
+    ix->stat_overflow_reason = f_over;
+    if (c.tensor && f_over == 1 && ix->rec_boost == 1) {
       ix->rec_boost = 4;
-    else
+      ix->epoch += 1;
+      ix->drop_graphs();
+    } else {
       safe = true;
+    }
   }
   return 0;
 }
 
-}  // namespace sss
-
-extern "C" int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
-                                float* D, int64_t* I, int out_on_device, void* stream) {
-  SSS_REQUIRE(ix != nullptr, "sss_index_search: NULL index");
-  SSS_REQUIRE(k >= 1, "sss_index_search: k must be >= 1");
-  SSS_REQUIRE(nq >= 0, "sss_index_search: negative nq");
-  SSS_REQUIRE(mode >= 0 && mode <= 2, "sss_index_search: unknown mode");
+static int search_all(sss_index* ix, const float* q, int64_t nq, int k, int mode, int q_on_device, float* D, int64_t* I,
+                      int out_on_device, void* stream, const char* who) {
+  SSS_REQUIRE(ix != nullptr, std::string(who) + ": NULL index");
+  SSS_REQUIRE(k >= 1, std::string(who) + ": k must be >= 1");
+  SSS_REQUIRE(nq >= 0, std::string(who) + ": negative nq");
+  SSS_REQUIRE(mode >= 0 && mode <= 2, std::string(who) + ": unknown mode");
   if (nq == 0) return 0;
-  SSS_REQUIRE(q && D && I, "sss_index_search: NULL buffer");
+  SSS_REQUIRE(q && D && I, std::string(who) + ": NULL buffer");
   DeviceGuard g(ix->device);
-  SSS_REQUIRE(g.ok, "sss_index_search: cudaSetDevice failed");
+  SSS_REQUIRE(g.ok, std::string(who) + ": cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   ix->stat_kernels = ix->stat_waves = ix->stat_reruns = 0;
   ix->scan_us = 0.0;
@@ -632,6 +810,25 @@ extern "C" int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int
     if (search_batch(ix, b, st)) return 1;
   }
   return 0;
+}
+
+}  // namespace sss
+
+extern "C" int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
+                                float* D, int64_t* I, int out_on_device, void* stream) {
+  return search_all(ix, q, nq, k, mode, q_on_device, D, I, out_on_device, stream, "sss_index_search");
+}
+
+// Bytes of one rank's packed candidate block [ids int64 nq*k | scores fp32 nq*k], padded to 16 bytes: the unit of
+// the sharded search's single all-gather.
+extern "C" int64_t sss_packed_bytes(int64_t nq, int k) { return (nq * k * 12 + 15) / 16 * 16; }
+
+extern "C" int sss_index_search_packed(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
+                                       void* packed, void* stream) {
+  SSS_REQUIRE(packed != nullptr, "sss_index_search_packed: NULL buffer");
+  int64_t* I = (int64_t*)packed;
+  float* D = (float*)((char*)packed + (size_t)nq * k * 8);
+  return search_all(ix, q, nq, k, mode, q_on_device, D, I, 1, stream, "sss_index_search_packed");
 }
 
 extern "C" int sss_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, int on_device, int device,
@@ -683,7 +880,19 @@ extern "C" int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_
   SSS_REQUIRE(n_shards >= 1 && k >= 1 && nq >= 0, "sss_topk_merge: bad shape");
   DeviceGuard g(device);
   SSS_REQUIRE(g.ok, "sss_topk_merge: cudaSetDevice failed");
-  return launch_topk_merge(cand_D, cand_I, n_shards, nq, k, metric, D, I, (cudaStream_t)stream);
+  return launch_topk_merge(cand_D, cand_I, nq * k, nq * k, n_shards, nq, k, metric, D, I, (cudaStream_t)stream);
+}
+
+extern "C" int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k, int metric, float* D,
+                                     int64_t* I, int device, void* stream) {
+  SSS_REQUIRE(gathered && D && I, "sss_topk_merge_packed: NULL buffer");
+  SSS_REQUIRE(n_shards >= 1 && k >= 1 && nq >= 0, "sss_topk_merge_packed: bad shape");
+  DeviceGuard g(device);
+  SSS_REQUIRE(g.ok, "sss_topk_merge_packed: cudaSetDevice failed");
+  const int64_t block = sss_packed_bytes(nq, k);
+  const int64_t* cI = (const int64_t*)gathered;
+  const float* cD = (const float*)((const char*)gathered + (size_t)nq * k * 8);
+  return launch_topk_merge(cD, cI, block / 4, block / 8, n_shards, nq, k, metric, D, I, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -832,7 +1041,7 @@ extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64
     ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
     ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
     ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.l2_tensor = 0; ra.lazy = 0; ra.final = 1; ra.row_limit = ix->n; ra.debug = nullptr;
-    std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1);
+    std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1, false, 0, Tuning());
     int64_t begin = 0;
     for (int64_t end : ends) {
       if (rc) break;

@@ -26,6 +26,25 @@ void set_error(const std::string& msg);
     }                              \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: every launcher remembers what it has set
+// per device (a process may hold handles on several GPUs), under a lock (handles on different threads).
+struct SmemAttr {
+  int set[64] = {0};
+  template <typename F>
+  int ensure(F* fn, int bytes) {
+    int dev = 0;
+    SSS_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 63;
+    int cur = __atomic_load_n(&set[dev], __ATOMIC_ACQUIRE);
+    if (cur >= bytes) return 0;
+    SSS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    // (two racing threads both set an attribute that only ever grows; the larger value wins below)
+    while (cur < bytes && !__atomic_compare_exchange_n(&set[dev], &cur, bytes, false, __ATOMIC_RELEASE, __ATOMIC_ACQUIRE)) {
+    }
+    return 0;
+  }
+};
+
 // ---- candidate encoding -----------------------------------------------------------------------------
 // A candidate is one uint64: (order-preserving key of the fp32 score) << 32 | (0xFFFFFFFF - id).
 // Sorting these descending gives (score desc, id asc) — the order rule of the whole library.

@@ -641,7 +641,26 @@ extern "C" int sss_encoder_set_param(sss_encoder_t* e, const char* name, const f
 
 extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt, float* out, int32_t* nonfinite,
                                    void* stream) {
-  SSS_REQUIRE(e && bt && out, "sss_encoder_forward: NULL argument");
+  sss_encoder_io_t io;
+  io.out = out;
+  io.z_query = nullptr;
+  io.z_product = nullptr;
+  io.run_gnn = 1;
+  io.run_pooling = 1;
+  io.nonfinite = nonfinite;
+  return sss_encoder_forward_ex(e, bt, &io, stream);
+}
+
+extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t* bt, const sss_encoder_io_t* io,
+                                      void* stream) {
+  SSS_REQUIRE(e && bt && io, "sss_encoder_forward: NULL argument");
+  float* out = io->out;
+  int32_t* nonfinite = io->nonfinite;
+  const bool run_gnn = io->run_gnn != 0, run_pool = io->run_pooling != 0;
+  SSS_REQUIRE(run_gnn || run_pool, "sss_encoder_forward_ex: nothing to run");
+  SSS_REQUIRE(!run_pool || out != nullptr, "sss_encoder_forward_ex: the pooling stage needs `out`");
+  SSS_REQUIRE(run_gnn || (io->z_query && io->z_product), "sss_encoder_forward_ex: pooling alone needs z_query / z_product");
+  SSS_REQUIRE(run_pool || (io->z_query && io->z_product), "sss_encoder_forward_ex: the GNN stage alone needs z_query / z_product");
   const int IN = e->sh.in_dim, H = e->sh.hidden, L = e->sh.n_layers, OUT = e->sh.out_dim, MSL = e->sh.max_seq_len;
   const int LIN = OUT - MSL, ZD = IN + L * H;
   const int B = (int)bt->n_graphs, NQ = (int)bt->n_query, NP = (int)bt->n_product, NE = (int)bt->n_expanded;
@@ -661,10 +680,11 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
   if (ws_begin(e, st)) return 1;
 
   // ---- workspace
-  float *Zq, *Zp, *Sq, *Sp, *as_q, *ad_q, *as_p, *ad_p, *Gp, *Agg, *gi, *gh, *uq_lin, *up_lin, *U, *coarse, *Aatt, *Bc, *att;
+  float *Zq = io->z_query, *Zp = io->z_product;  // node embeddings [N, in + layers * hidden]: the caller's or ours
+  float *Sq, *Sp, *as_q, *ad_q, *as_p, *ad_p, *Gp, *Agg, *gi, *gh, *uq_lin, *up_lin, *U, *coarse, *Aatt, *Bc, *att;
   int *cnt_i, *cnt_pre, *cursor_tmp, *occ_prod, *node_graph, *ranges;
   const int NT = NE + NQ;
-  if (ws_alloc(e, &Zq, (size_t)NQ * ZD) || ws_alloc(e, &Zp, (size_t)NP * ZD) || ws_alloc(e, &Sq, (size_t)NQ * 2 * H) ||
+  if ((!Zq && ws_alloc(e, &Zq, (size_t)NQ * ZD)) || (!Zp && ws_alloc(e, &Zp, (size_t)NP * ZD)) || ws_alloc(e, &Sq, (size_t)NQ * 2 * H) ||
       ws_alloc(e, &Sp, (size_t)NP * 3 * H) || ws_alloc(e, &as_q, NQ) || ws_alloc(e, &ad_q, NQ) || ws_alloc(e, &as_p, NP) ||
       ws_alloc(e, &ad_p, NP) || ws_alloc(e, &Gp, (size_t)NP * H) || ws_alloc(e, &Agg, (size_t)NP * H) ||
       ws_alloc(e, &gi, (size_t)NP * 3 * H) || ws_alloc(e, &gh, (size_t)NP * 3 * H) ||
@@ -674,23 +694,25 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
       ws_alloc(e, &cnt_pre, NP + 1) || ws_alloc(e, &cursor_tmp, NP + 1) || ws_alloc(e, &occ_prod, NE + 1) ||
       ws_alloc(e, &node_graph, NT) || ws_alloc(e, &ranges, (size_t)B * 4))
     return 1;
-  if (nonfinite) {
-    SSS_CUDA_OK(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t), st));
+  if (nonfinite) SSS_CUDA_OK(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t), st));
+  if (nonfinite && run_gnn) {
     nan_flag_kernel<<<(unsigned)(((int64_t)NQ * IN + 255) / 256), 256, 0, st>>>(bt->x_query, (int64_t)NQ * IN, nonfinite);
     nan_flag_kernel<<<(unsigned)(((int64_t)NP * IN + 255) / 256), 256, 0, st>>>(bt->x_product, (int64_t)NP * IN, nonfinite);
   }
-  copy_cols_kernel<<<(unsigned)(((int64_t)NQ * IN + 255) / 256), 256, 0, st>>>(bt->x_query, NQ, IN, Zq, ZD);
-  copy_cols_kernel<<<(unsigned)(((int64_t)NP * IN + 255) / 256), 256, 0, st>>>(bt->x_product, NP, IN, Zp, ZD);
-
-  // ---- graph structure, shared by the three layers
   Csr qp, pq, pp;
-  const int n_loop = NQ < NP ? NQ : NP;
-  if (build_csr(e, bt->qp_src, bt->qp_dst, bt->e_qp, NP, 1, n_loop, &qp, st)) return 1;   // dst = product
-  if (build_csr(e, bt->pq_src, bt->pq_dst, bt->e_pq, NQ, 1, n_loop, &pq, st)) return 1;   // dst = query
-  if (build_csr(e, bt->pp_src, bt->pp_dst, bt->e_pp, NP, 0, 0, &pp, st)) return 1;        // dst = product
+  if (run_gnn) {
+    SSS_REQUIRE(bt->x_query && bt->x_product, "sss_encoder_forward: the GNN stage needs x_query / x_product");
+    copy_cols_kernel<<<(unsigned)(((int64_t)NQ * IN + 255) / 256), 256, 0, st>>>(bt->x_query, NQ, IN, Zq, ZD);
+    copy_cols_kernel<<<(unsigned)(((int64_t)NP * IN + 255) / 256), 256, 0, st>>>(bt->x_product, NP, IN, Zp, ZD);
+    // ---- graph structure, shared by the three layers
+    const int n_loop = NQ < NP ? NQ : NP;
+    if (build_csr(e, bt->qp_src, bt->qp_dst, bt->e_qp, NP, 1, n_loop, &qp, st)) return 1;   // dst = product
+    if (build_csr(e, bt->pq_src, bt->pq_dst, bt->e_pq, NQ, 1, n_loop, &pq, st)) return 1;   // dst = query
+    if (build_csr(e, bt->pp_src, bt->pp_dst, bt->e_pp, NP, 0, 0, &pp, st)) return 1;        // dst = product
+  }
 
-  // ---- HeteroGGNN layers
-  for (int l = 0; l < L; ++l) {
+  // ---- HeteroGGNN layers (model/gnn.py:64-81)
+  for (int l = 0; run_gnn && l < L; ++l) {
     const int cin = l == 0 ? IN : H;
     e->a_split.clear();  // activation splits are keyed by pointer and buffers such as Agg are rewritten every layer
     const int off = l == 0 ? 0 : IN + (l - 1) * H;
@@ -732,7 +754,11 @@ extern "C" int sss_encoder_forward(sss_encoder_t* e, const sss_graph_batch_t* bt
                                                                                Zp + off_next, ZD);
   }
 
-  // ---- PositionalAttentionPooling
+  if (!run_pool) {
+    SSS_CUDA_OK(cudaGetLastError());
+    return ws_end(e, st);
+  }
+  // ---- PositionalAttentionPooling (model/gnn.py:193-217)
   e->a_split.clear();
   const float *wq = P(e, "pooling.query_lin.weight", (int64_t)LIN * ZD), *bq = P(e, "pooling.query_lin.bias", LIN),
               *wp = P(e, "pooling.product_lin.weight", (int64_t)LIN * ZD), *bp = P(e, "pooling.product_lin.bias", LIN),

@@ -201,11 +201,8 @@ int launch_gemm_bf16x3(const void* a_hi, const void* a_lo, int m_pad, const void
   if (make_tensor_map_bf16_2d(tm[1], a_lo, (uint64_t)m_pad, (uint64_t)k_pad, 128)) return 1;
   if (make_tensor_map_bf16_2d(tm[2], b_hi, (uint64_t)n_pad, (uint64_t)k_pad, 128)) return 1;
   if (make_tensor_map_bf16_2d(tm[3], b_lo, (uint64_t)n_pad, (uint64_t)k_pad, 128)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    attr_set = true;
-  }
+  static SmemAttr attr;  // per device
+  if (attr.ensure(gemm_bf16x3_kernel, kGemmSmemBytes)) return 1;
   GemmParams p;
   p.C = C;
   p.M = M;

@@ -10,9 +10,14 @@ namespace sss {
 // prep.cu
 int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode, float* out_f32, void* out_bf16,
                     int64_t out_row0, unsigned int* maxnorm2_bits, cudaStream_t st, int aug = 0);
-// stats[0] = bits of max ||row||^2, stats[1] = bits of max ||row - bf16(row)||^2 (both from launch_add_rows)
-int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
-                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug = 0);
+// stats[0] = bits of max ||row||^2, stats[1] = bits of max ||row - bf16(row)||^2, stats[2] = bits of max ||row||_4^4
+// (all from launch_add_rows)
+// q_keep (optional, fp32 [nq_pad, d]): a private copy of the queries for the re-scoring passes (the caller's buffer
+// is only read by this kernel, which is what lets a captured search graph re-bind one pointer per call)
+// slack: 0 none, 1 rigorous bound (EXACT), 2 statistical bound (BF16) — see prep.cu
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int slack,
+                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug = 0,
+                        float* q_keep = nullptr);
 int launch_gather_rows(const float* table, int64_t n_rows, int d, const int64_t* ids, int64_t n, float* out, int* bad,
                        cudaStream_t st);
 int launch_row_seg(const int64_t* seg_off, int64_t n_seg, int32_t* row_seg, cudaStream_t st);
@@ -44,14 +49,14 @@ struct Bf16ScanPlan {
 };
 // rec_boost multiplies the records per sub-region (1, or 4 after a search that overflowed one)
 // d_used = columns that hold data (d, + 2 for L2); 0 = d_pad
+// variant: 0 automatic (pair kernel above 128 queries, TS below), 1 SS, 2 TS, 3 pair — a tuning knob of the handle
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost = 1,
-                   int d_used = 0);
+                   int d_used = 0, int variant = 0);
 // tensor maps are CUtensorMap objects (128 bytes each) built by make_tensor_map_2d
 int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, uint64_t cols_pad, uint32_t box_rows);
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream);
-unsigned long long* scan_prof_buffer();  // experiments only (SSS_SCAN_PROF)
 // gemm_bf16x3_sm100.cu — split-bf16 tensor-core GEMM of the encoder: C[M,N] = A[M,K] * B[N,K]^T
 int launch_split_bf16(const float* x, int rows, int cols, int64_t ld, int transposed, void* hi, void* lo, int rows_pad,
                       int cols_pad, cudaStream_t stream);
@@ -89,8 +94,12 @@ struct RefineArgs {
 int launch_refine(const RefineArgs& a, SelectState st, int num_sms, cudaStream_t stream);
 int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
                 cudaStream_t stream);
-int launch_topk_merge(const float* cD, const int64_t* cI, int n_shards, int64_t nq, int k, int metric, float* D,
-                      int64_t* I, cudaStream_t stream);
+// shard s: scores at cD + s * stride_d, ids at cI + s * stride_i (element strides)
+int launch_topk_merge(const float* cD, const int64_t* cI, int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
+                      int k, int metric, float* D, int64_t* I, cudaStream_t stream);
+// addresses of the two kernels whose pointer arguments a captured search graph re-binds per call (api.cu)
+const void* emit_kernel_addr();
+const void* prep_queries_kernel_addr();
 
 // binary.cu
 int launch_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits, cudaStream_t st);

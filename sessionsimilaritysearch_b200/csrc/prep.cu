@@ -44,12 +44,13 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
     den[tid] = dn;
     if (maxnorm2_bits) {
       // ||x - bf16(x)||^2 of the stored row: the exact rounding error the tensor-core scan will see
-      float e2 = 0.0f, n2y = 0.0f;
+      float e2 = 0.0f, n2y = 0.0f, n4y = 0.0f;
       for (int j = 0; j < d; ++j) {
         const float y = norm_mode == 0 ? x[j] : __fdiv_rn(x[j], dn);
         const float r = y - __bfloat162float(__float2bfloat16_rn(y));
         e2 = __fmaf_rn(r, r, e2);
         n2y = __fmaf_rn(y, y, n2y);
+        n4y = __fmaf_rn(y * y, y * y, n4y);
       }
       if (aug) {
         // -||y||^2 / 2 in TWO bf16 columns (hi + lo: 16 mantissa bits — one column would put 2^-9 * ||y||^2 / 2 of
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(128) add_rows_kernel(const float* __restrict__
       }
       atomicMax(maxnorm2_bits, __float_as_uint(n2 * 1.00002f + 1e-30f));
       atomicMax(maxnorm2_bits + 1, __float_as_uint(e2 * 1.00002f + 1e-30f));
+      atomicMax(maxnorm2_bits + 2, __float_as_uint(n4y * 1.00002f + 1e-30f));  // max ||y||_4^4 (statistical slack)
     }
   }
   __syncthreads();
@@ -105,7 +107,8 @@ int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode,
   if (rpb < 1) rpb = 1;
   size_t smem = sizeof(float) * ((size_t)rpb * (d + 1) + 2 * (size_t)rpb);
   SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for add_rows_kernel");
-  SSS_CUDA_OK(cudaFuncSetAttribute(add_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static SmemAttr attr;
+  if (attr.ensure(add_rows_kernel, (int)smem)) return 1;
   int64_t blocks = (n + rpb - 1) / rpb;
   add_rows_kernel<<<(unsigned)blocks, 128, smem, st>>>(in, n, d, d_pad, norm_mode, rpb, out_f32,
                                                         (__nv_bfloat16*)out_bf16, out_row0, maxnorm2_bits, aug);
@@ -113,46 +116,65 @@ int launch_add_rows(const float* in, int64_t n, int d, int d_pad, int norm_mode,
   return 0;
 }
 
-// Query staging: bf16 copy (zero padded to [nq_pad, d_pad]), filter slack, selection state reset.
+// Query staging: bf16 copy (zero padded to [nq_pad, d_pad]), private fp32 copy, filter slack, selection state reset.
 // One warp per query row.
 //
-// EXACT-mode slack.  Let s be the fixed-order fp32 score of (q, x) and b the tensor-core score of the bf16
-// copies (q^, x^).  q.x - q^.x^ = q.(x - x^) + (q - q^).x^, so
-//     |s - b| <= ||q|| * max_rows ||x - x^||  +  ||q - q^|| * max_rows ||x^||  +  accumulation slack,
-// with the two maxima measured exactly when rows are added (stats[1], stats[0]) and the query terms measured
-// here; the accumulation slack covers d fp32 roundings on our side and a generous 8x that inside the tensor
-// core.  This is a rigorous bound, about 2.3x tighter than 2^-7 * ||q|| * ||x||.
+// Filter slack.  Let s be the fixed-order fp32 score of (q, x) and b the tensor-core score of the bf16
+// copies (q^, x^).  q.x - q^.x^ = q.(x - x^) + (q - q^).x^.
+//   slack == 1 (SSS_MODE_EXACT): the rigorous bound
+//       |s - b| <= ||q|| * max_rows ||x - x^||  +  ||q - q^|| * max_rows ||x^||  +  accumulation slack,
+//     with the two maxima measured exactly when rows are added (stats[1], stats[0]) and the query terms measured
+//     here; the accumulation slack covers d fp32 roundings on our side and a generous 8x that inside the tensor
+//     core.  About 2.3x tighter than 2^-7 * ||q|| * ||x||.
+//   slack == 2 (SSS_MODE_BF16): a statistical bound.  The bf16 rounding error of element i is at most 2^-9 |x_i|;
+//     modelled as independent and uniform in that range, s - b has variance
+//         <= (2^-18 / 3) * (sum q_i^2 x_i^2 + sum q_i^2 x^_i^2) <= (2^-17 / 3) * ||q||_4^2 * max_rows ||x||_4^2
+//     (Cauchy-Schwarz; max ||x||_4^4 measured at add time, stats[2]).  The slack is 4 of those standard deviations
+//     plus the accumulation term, never more than the rigorous bound.  For embedding-like rows it is ~2x tighter at
+//     d = 128 and ~10x at d = 1600 (the rigorous bound grows like sqrt(d) relative to the actual noise).
 __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad, int d, int d_pad,
-                                    __nv_bfloat16* __restrict__ q_bf16, int exact, const unsigned int* stats,
-                                    SelectState st, int aug) {
+                                    __nv_bfloat16* __restrict__ q_bf16, int slack, const unsigned int* stats,
+                                    SelectState st, int aug, float* __restrict__ q_keep) {
   const int warps_per_block = blockDim.x / 32;
   const int64_t row = (int64_t)blockIdx.x * warps_per_block + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= nq_pad) return;
-  float ss = 0.0f, ee = 0.0f;
+  float ss = 0.0f, ee = 0.0f, s4 = 0.0f;
   for (int j = lane; j < d_pad; j += 32) {
     float v = (row < nq && j < d) ? q[row * (int64_t)d + j] : 0.0f;
+    if (q_keep != nullptr && j < d) q_keep[row * (int64_t)d + j] = v;
     const bool one = aug && (j == d || j == d + 1) && row < nq;  // L2 on the tensor path: query side of the extra columns
     if (one) v = 1.0f;
     const __nv_bfloat16 vb = __float2bfloat16_rn(v);
     const float r = v - __bfloat162float(vb);
-    if (!one) ss += v * v;
+    if (!one) {
+      ss += v * v;
+      s4 += (v * v) * (v * v);
+    }
     ee += r * r;
     if (q_bf16) q_bf16[row * (int64_t)d_pad + j] = vb;
   }
   for (int o = 16; o > 0; o >>= 1) {
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
     ee += __shfl_xor_sync(0xffffffffu, ee, o);
+    s4 += __shfl_xor_sync(0xffffffffu, s4, o);
   }
   if (lane == 0) {
     float m = 0.0f;
-    if (exact && stats != nullptr) {
+    if (slack != 0 && stats != nullptr) {
       const float xn = sqrtf(__uint_as_float(stats[0]));   // max ||x||   (inflated at add time)
       const float xe = sqrtf(__uint_as_float(stats[1]));   // max ||x - x^||
       const float qn = sqrtf((ss + (aug ? 2.0f : 0.0f)) * 1.0001f), qe = sqrtf(ee * 1.0001f);
-      m = (qn * xe + qe * (xn + xe)) * 1.0001f + (float)d * 5.4e-7f * qn * xn + 1e-30f;
+      const float acc_slack = (float)d * 5.4e-7f * qn * xn + 1e-30f;
+      m = (qn * xe + qe * (xn + xe)) * 1.0001f + acc_slack;
       // (the conversion -dist = 2 * score - ||q||^2 uses this kernel's own ||q||^2: its rounding is part of the slack)
       if (aug) m += 4e-7f * (ss + 2.0f);
+      if (slack == 2 && !aug) {
+        const float x4 = sqrtf(sqrtf(__uint_as_float(stats[2])));  // max ||x||_4
+        const float q4 = sqrtf(sqrtf(s4 * 1.0001f));
+        const float sigma = 1.5946e-3f * q4 * x4;                  // sqrt(2^-17 / 3) = 1.5946e-3
+        m = fminf(m, 4.0f * sigma + acc_slack);
+      }
     }
     st.margin[row] = m;
     if (st.qn2 != nullptr) st.qn2[row] = ss;
@@ -167,12 +189,14 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int64_t nq, int
   }
 }
 
-int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int exact,
-                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug) {
+const void* prep_queries_kernel_addr() { return (const void*)prep_queries_kernel; }
+
+int launch_prep_queries(const float* q, int64_t nq, int64_t nq_pad, int d, int d_pad, void* q_bf16, int slack,
+                        const unsigned int* stats, SelectState st, cudaStream_t stream, int aug, float* q_keep) {
   const int wpb = 8;
   int64_t blocks = (nq_pad + wpb - 1) / wpb;
   prep_queries_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(q, nq, nq_pad, d, d_pad, (__nv_bfloat16*)q_bf16,
-                                                                  exact, stats, st, aug);
+                                                                  slack, stats, st, aug, q_keep);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -28,8 +28,6 @@
 // stream) below.
 #include <cuda.h>
 #include <cuda_bf16.h>
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_sm100.cuh"
@@ -49,8 +47,6 @@ struct ScanParams {
   int rec_cap;
   int* err_flag;
   const uint4* q_bf16;   // [nq_pad, d_pad] bf16, 16-byte aligned rows (TS variant reads it directly)
-  unsigned long long* prof;  // experiments only: [0] MMA wait tempty, [1] MMA wait full, [2] MMA issue, [3] epi wait tfull, [4] epi work, [5] units
-  int dbg;               // experiments only (SSS_SCAN_DBG): 1 = read half of the accumulator columns, 2 = read all, test half
   float* cmax;           // bootstrap mode: write the max of every 32-row chunk to cmax[chunk * nq_pad + q] instead
                          // of filtering (chunk counted from row_begin)
   int groups;            // K-loop variant: query groups of 256 (one per CTA pair)
@@ -310,7 +306,7 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
     if (lane == 0 && my_tiles > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < my_tiles && p.dbg != 5 && p.dbg != 8; ++it) {
+      for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(empty_bar + 8 * stage, phase ^ 1u, p.err_flag, 201);
         mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.num_kb * kKBlockBytes);
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -329,50 +325,25 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
       uint32_t u = 0;
       int stage = 0;
       uint32_t phase = 0;
-      long long w_empty = 0, w_full = 0, t_issue = 0;
-      unsigned long long g0t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0t));
-      const long long cl0 = clock64();
       for (int it = 0; it < my_tiles; ++it) {
-        long long c0 = clock64();
-        if (p.dbg != 5 && p.dbg != 8) mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 203);
+        mbar_wait(full_bar + 8 * stage, phase, p.err_flag, 203);
         tc_fence_after();
-        w_full += clock64() - c0;
         for (int mt = 0; mt < num_mt; ++mt, ++u) {
           const uint32_t slot = u & 1u;
-          c0 = clock64();
-          if (p.dbg != 8) mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 204);
+          mbar_wait(tempty_bar + 8 * slot, ((u >> 1) & 1u) ^ 1u, p.err_flag, 204);
           tc_fence_after();
-          const long long c1 = clock64();
-          w_empty += c1 - c0;
           const uint32_t d_tmem = d_base + slot * (uint32_t)kTileRows;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(mt * p.num_kb + kb) * 32u;
             const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
-            // experiments (SSS_SCAN_DBG): 3 = issue half of the MMAs, 4 = all MMAs at N=64 (half the work each)
-            const int k4_end = p.dbg == 3 ? 2 : 4;
-            const uint32_t idesc = p.dbg == 4 ? ((kIdesc & ~(0x3Fu << 17)) | ((64u >> 3) << 17)) : kIdesc;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)  // K=16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-              if (k4 < k4_end)
-                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u,
-                             idesc);
+              umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
           }
           umma_commit(tfull_bar + 8 * slot);
-          t_issue += clock64() - c1;
         }
         umma_commit(empty_bar + 8 * stage);
         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-      }
-      if (p.prof != nullptr && lane == 0) {
-        atomicAdd(&p.prof[0], (unsigned long long)w_empty);
-        atomicAdd(&p.prof[1], (unsigned long long)w_full);
-        atomicAdd(&p.prof[2], (unsigned long long)t_issue);
-        atomicAdd(&p.prof[5], (unsigned long long)u);
-        unsigned long long g1t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1t));
-        atomicAdd(&p.prof[6], g1t - g0t);
-        atomicAdd(&p.prof[7], (unsigned long long)(clock64() - cl0));
       }
     }
   } else if (warp >= 4) {
@@ -419,10 +390,8 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
       HitRecord* myrec = p.rec + ((size_t)qidx * sub_stride + my_sub) * (size_t)kCap;
       mt += 2;
       while (mt >= num_mt) { mt -= num_mt; ++it; }
-      const long long e0 = clock64();
       mbar_wait(tfull_bar + 8 * slot, ph, p.err_flag, 205);
       tc_fence_after();
-      if (p.prof != nullptr && ew == 0 && lane == 0) atomicAdd(&p.prof[3], (unsigned long long)(clock64() - e0));
       const uint32_t taddr = d_base + lane_base + slot * (uint32_t)kTileRows;
       auto process = [&](const uint32_t (&r)[32], int c) {
         float f[32];
@@ -455,35 +424,22 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
           }
         }
       };
-      if (p.dbg == 6 || p.dbg == 8) {  // experiment: barrier handshakes only
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
-        continue;
-      }
       uint32_t ra[32], rb[32];
       tmem_ld32(taddr, ra);
       tmem_ld_wait();
       tmem_ld32(taddr + 32u, rb);
       process(ra, 0);
       tmem_ld_wait();
-      if (p.dbg == 1) {  // experiment: half of the TMEM reads
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
-        process(rb, 1);
-        continue;
-      }
       tmem_ld32(taddr + 64u, ra);
       process(rb, 1);
       tmem_ld_wait();
       tmem_ld32(taddr + 96u, rb);
-      if (p.dbg != 2) process(ra, 2);
+      process(ra, 2);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
-      if (p.dbg != 2) process(rb, 3);
+      process(rb, 3);
     }
     for (int m = 0; m < num_mt; ++m) {
       const uint32_t qidx = (uint32_t)((mt_base + m) * kTileQ + quarter * 32 + lane);
@@ -1007,7 +963,7 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
 }
 
 int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16ScanPlan* plan, int rec_boost,
-                   int d_used) {
+                   int d_used, int variant) {
   SSS_REQUIRE(d_pad % 64 == 0 && d_pad >= 64 && d_pad <= 4096, "tensor-core scan supports d <= 4096");
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
@@ -1050,14 +1006,12 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   plan->num_mt = (total_mtiles + plan->grid_y - 1) / plan->grid_y;
   plan->grid_x = num_sms / plan->grid_y;
   if (plan->grid_x < 1) plan->grid_x = 1;
-  const char* force_ss = getenv("SSS_SCAN_SS");
-  const char* variant = getenv("SSS_SCAN_VARIANT");  // "2cta" (default), "ts", "ss"
-  plan->ts = !(force_ss && force_ss[0] == '1');  // A operand from TMEM unless the SS form is forced
-  plan->two_cta = !(variant && (variant[0] == 't' || variant[0] == 's')) && !(force_ss && force_ss[0] == '1');
+  // variant (a tuning knob read once per handle, SSS_SCAN_VARIANT): 0 automatic, 1 SS, 2 TS, 3 pair
+  plan->ts = variant != 1;  // A operand from TMEM unless the SS form is forced
+  plan->two_cta = variant == 0 || variant == 3;
   // one m-tile (<= 128 queries) is the DB-stream-bound regime: independent 1-CTA tiles with the queries in TMEM
   // reach 0.86 of the HBM copy bandwidth, the pair kernel (half of every MMA is padding there) 0.77
-  if (total_mtiles == 1 && !(variant && variant[0] == '2')) plan->two_cta = false;
-  if (variant && variant[0] == 's') plan->ts = false;
+  if (total_mtiles == 1 && variant != 3) plan->two_cta = false;
   if (plan->two_cta) {
     // pairs of CTAs: every pair holds up to 8 m-tiles (4 per CTA) and walks 256-row DB tiles
     plan->ts = false;
@@ -1099,9 +1053,6 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   return 0;
 }
 
-static unsigned long long* g_scan_prof = nullptr;
-unsigned long long* scan_prof_buffer() { return g_scan_prof; }
-
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream) {
@@ -1124,32 +1075,20 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   p.cmax = cmax;
   p.groups = plan.groups;
   p.last_k4 = plan.last_k4;
-  {
-    const char* dbg = getenv("SSS_SCAN_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
-    p.prof = nullptr;
-    if (getenv("SSS_SCAN_PROF")) {
-      if (!g_scan_prof) {
-        SSS_CUDA_OK(cudaMalloc((void**)&g_scan_prof, 8 * sizeof(unsigned long long)));
-        SSS_CUDA_OK(cudaMemset(g_scan_prof, 0, 8 * sizeof(unsigned long long)));
-      }
-      p.prof = g_scan_prof;
-    }
-  }
   if (p.n_tiles <= 0) return 0;
   const bool big = plan.rec_cap != kRecSubCap && !plan.kloop;  // boosted sub-regions (after an overflow): 4x
   SSS_REQUIRE(plan.kloop || plan.rec_cap == kRecSubCap || plan.rec_cap == 4 * kRecSubCap, "unsupported record capacity");
-  static int smem_set = 0;
-  if (smem_set < plan.smem_bytes) {
-    const int sb = plan.smem_bytes;
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_ts_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel<kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_2cta_kernel<4 * kRecSubCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    SSS_CUDA_OK(cudaFuncSetAttribute(scan_bf16_kloop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    smem_set = sb;
+  // (per device, per kernel: the attribute lives in the device's context)
+  static SmemAttr a_ss, a_ss4, a_ts, a_ts4, a_pair, a_pair4, a_kloop;
+  const int sb = plan.smem_bytes;
+  if (plan.kloop) {
+    if (a_kloop.ensure(scan_bf16_kloop_kernel, sb)) return 1;
+  } else if (plan.two_cta) {
+    if (big ? a_pair4.ensure(scan_bf16_2cta_kernel<4 * kRecSubCap>, sb) : a_pair.ensure(scan_bf16_2cta_kernel<kRecSubCap>, sb)) return 1;
+  } else if (plan.ts) {
+    if (big ? a_ts4.ensure(scan_bf16_ts_kernel<4 * kRecSubCap>, sb) : a_ts.ensure(scan_bf16_ts_kernel<kRecSubCap>, sb)) return 1;
+  } else {
+    if (big ? a_ss4.ensure(scan_bf16_kernel<4 * kRecSubCap>, sb) : a_ss.ensure(scan_bf16_kernel<kRecSubCap>, sb)) return 1;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
   const CUtensorMap& mq = *(const CUtensorMap*)tmap_q;

@@ -172,7 +172,10 @@ __device__ __forceinline__ int warp_append(int* counter, bool pass) {
   return pass ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
 
-// optional per-phase cycle accounting of thread 0 (a.debug[4 + phase], profiling builds of the statistics only)
+// per-phase cycle accounting of thread 0 (a.debug[4 + phase]): experiment builds only (-DSSS_EXPERIMENT); release
+// kernels carry no clock reads
+#ifdef SSS_EXPERIMENT
+#define RF_PHASE_BEGIN() long long _t0 = clock64()
 #define RF_PHASE(i)                                                              \
   do {                                                                           \
     if (a.debug != nullptr && threadIdx.x == 0) {                                \
@@ -181,10 +184,14 @@ __device__ __forceinline__ int warp_append(int* counter, bool pass) {
       _t0 = _t;                                                                  \
     }                                                                            \
   } while (0)
+#else
+#define RF_PHASE_BEGIN() do { } while (0)
+#define RF_PHASE(i) do { } while (0)
+#endif
 
 template <class C>
 __device__ int refine_query(const RefineArgs& a, const SelectState& st, const RefineSmem<C>& sm, int q) {
-  long long _t0 = clock64();
+  RF_PHASE_BEGIN();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int NW = C::kThreads / 32;
@@ -602,28 +609,20 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
   SSS_REQUIRE(st.cap <= RefineLarge::kSlots, "candidate capacity too large for refine");
   SSS_REQUIRE(a.k <= RefineLarge::kKmax, "k too large for refine");
   SSS_REQUIRE(a.rec == nullptr || a.rec_nsub <= RefineLarge::kMaxSub, "too many record sub-regions per query");
-  static size_t smem_small = 0, smem_large = 0;
+  static SmemAttr attr_small, attr_large;  // per device
   a.all_large = a.k > RefineSmall::kKmax / 2 ? 1 : 0;
   if (!a.all_large) {
     const int d_round = (a.d + RefineSmall::kKc - 1) / RefineSmall::kKc * RefineSmall::kKc;
     const size_t smem = RefineSmall::smem_bytes(d_round, a.rescore != 0);
     SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
-    if (smem > smem_small) {
-      SSS_CUDA_OK(cudaFuncSetAttribute(refine_small_kernel<RefineSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-      smem_small = smem;
-    }
+    if (attr_small.ensure(refine_small_kernel<RefineSmall>, (int)smem)) return 1;
     refine_small_kernel<RefineSmall><<<(unsigned)a.nq, RefineSmall::kThreads, smem, stream>>>(a, st);
     SSS_CUDA_OK(cudaGetLastError());
   }
   const int d_round = (a.d + RefineLarge::kKc - 1) / RefineLarge::kKc * RefineLarge::kKc;
   const size_t smem = RefineLarge::smem_bytes(d_round, a.rescore != 0);
   SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
-  if (smem > smem_large) {
-    SSS_CUDA_OK(cudaFuncSetAttribute(refine_large_kernel<RefineLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    smem_large = smem;
-  }
+  if (attr_large.ensure(refine_large_kernel<RefineLarge>, (int)smem)) return 1;
   int grid = (int)std::min<int64_t>(a.nq, num_sms);
   refine_large_kernel<RefineLarge><<<grid, RefineLarge::kThreads, smem, stream>>>(a, st);
   SSS_CUDA_OK(cudaGetLastError());
@@ -636,65 +635,85 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
 // i.e. (with gap = floor((max session length + 30) / 32) + 1, or 1 without sessions) k rows of k DISTINCT
 // sessions/rows whose scores are >= T, the smallest of those maxima.  So the k-th best exact session score is >= T - margin and a row
 // can only matter if its tensor-core score is >= T - 2 * margin: thr = the float just below that.
-__global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq_pad,
-                                                            int k, int chunk_gap, float slack_mult, SelectState st) {
-  extern __shared__ uint32_t bs_keys[];  // [n_chunks]
-  __shared__ uint32_t hist[256];
-  __shared__ int s_bin, s_above;
-  const int q = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31;
+// One block = 8 consecutive queries: the chunk maxima are stored [chunk][query], so 8 threads read one full 32-byte
+// sector per chunk (a block per query read 4 of every 32 bytes it pulled: 128 MB of L2 traffic per 1000 queries);
+// then warp w radix-selects (4 x 8 bits, warp-synchronous) the need-th largest key of query w.
+constexpr int kBootQ = 8;
+__global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq,
+                                                            int64_t nq_pad, int k, int chunk_gap, float slack_mult,
+                                                            SelectState st) {
+  extern __shared__ uint32_t bs_keys[];  // [kBootQ][n_chunks + 8] (row pitch keeps the transposing stores conflict free)
+  __shared__ uint32_t hist_all[kBootQ][256];
+  const int pitch = n_chunks + 8;
+  const int64_t q0 = (int64_t)blockIdx.x * kBootQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // of the `need` largest chunks, taken in index order, every gap-th one is >= gap chunks from the previous pick
   const int need = (k - 1) * chunk_gap + 1;
   if (need > n_chunks) return;
-  for (int i = tid; i < n_chunks; i += blockDim.x) bs_keys[i] = score_key(cmax[(size_t)i * nq_pad + q]);
-  // radix select (4 x 8 bits) of the need-th largest key
+  {
+    const int qq = tid & 7;
+    for (int i = tid >> 3; i < n_chunks; i += 32)
+      bs_keys[qq * pitch + i] = score_key(cmax[(size_t)i * (size_t)nq_pad + (size_t)(q0 + qq)]);
+  }
+  __syncthreads();
+  const int64_t q = q0 + warp;
+  if (q >= nq) return;
+  const uint32_t* keys = bs_keys + warp * pitch;
+  uint32_t* hist = hist_all[warp];
   uint32_t prefix = 0u, mask = 0u;
   int want = need;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    hist[tid] = 0u;
-    __syncthreads();
-    for (int i = tid; i < n_chunks; i += blockDim.x) {
-      const uint32_t key = bs_keys[i];
+    for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+    __syncwarp();
+    for (int i = lane; i < n_chunks; i += 32) {
+      const uint32_t key = keys[i];
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
     }
-    __syncthreads();
-    if (tid < 32) {  // lane l owns bins [8l, 8l + 8); find the bin where the count from the top reaches `want`
-      int mine = 0;
+    __syncwarp();
+    // lane l owns bins [8l, 8l + 8); find the bin where the count from the top reaches `want`
+    int mine = 0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) mine += (int)hist[lane * 8 + b];
-      int above = mine;  // inclusive suffix sum over lanes >= l
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_down_sync(0xffffffffu, above, o);
-        if (lane + o < 32) above += t;
-      }
-      const int strictly_above = above - mine;  // counts in higher lanes
-      if (strictly_above < want && above >= want) {
-        int acc = strictly_above;
-        for (int b = 7; b >= 0; --b) {
-          const int c = (int)hist[lane * 8 + b];
-          if (acc + c >= want) {
-            s_bin = lane * 8 + b;
-            s_above = acc;
-            break;
-          }
-          acc += c;
+    for (int b = 0; b < 8; ++b) mine += (int)hist[lane * 8 + b];
+    int above = mine;  // inclusive suffix sum over lanes >= l
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, above, o);
+      if (lane + o < 32) above += t;
+    }
+    const int strictly_above = above - mine;  // counts in higher lanes
+    const bool owner = strictly_above < want && above >= want;
+    int bin = 0, acc_above = 0;
+    if (owner) {
+      int acc = strictly_above;
+      for (int b = 7; b >= 0; --b) {
+        const int c = (int)hist[lane * 8 + b];
+        if (acc + c >= want) {
+          bin = lane * 8 + b;
+          acc_above = acc;
+          break;
         }
+        acc += c;
       }
     }
-    __syncthreads();
-    want -= s_above;
-    prefix |= (uint32_t)s_bin << shift;
+    const uint32_t bal = __ballot_sync(0xffffffffu, owner);
+    const int src = __ffs(bal) - 1;  // exactly one owner: the counts from the top pass `want` in one lane
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    acc_above = __shfl_sync(0xffffffffu, acc_above, src);
+    want -= acc_above;
+    prefix |= (uint32_t)bin << shift;
     mask |= 0xFFu << shift;
-    __syncthreads();
+    __syncwarp();
   }
-  if (tid == 0) st.thr[q] = nextafterf(key_score(prefix) - slack_mult * st.margin[q], -INFINITY);
+  if (lane == 0) st.thr[q] = nextafterf(key_score(prefix) - slack_mult * st.margin[q], -INFINITY);
 }
 
 int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
                          float slack_mult, SelectState st, cudaStream_t stream) {
-  SSS_REQUIRE(n_chunks <= 8192, "bootstrap region too large");
-  bootstrap_thr_kernel<<<(unsigned)nq, 256, (size_t)n_chunks * 4, stream>>>(cmax, n_chunks, nq_pad, k, chunk_gap,
-                                                                           slack_mult, st);
+  SSS_REQUIRE(n_chunks <= 4096 && n_chunks % 32 == 0, "bootstrap region too large");
+  static SmemAttr attr;
+  const size_t smem = (size_t)kBootQ * (size_t)(n_chunks + 8) * 4;
+  if (attr.ensure(bootstrap_thr_kernel, (int)smem)) return 1;
+  bootstrap_thr_kernel<<<(unsigned)((nq + kBootQ - 1) / kBootQ), 256, smem, stream>>>(cmax, n_chunks, nq, nq_pad, k,
+                                                                                     chunk_gap, slack_mult, st);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -726,11 +745,16 @@ int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset
   return 0;
 }
 
+const void* emit_kernel_addr() { return (const void*)emit_kernel; }
+
 // ---- k-way merge of per-shard candidates (after the NCCL all-gather) ---------------------
-// One block per query; (key desc, id asc) bitonic sort of n_shards*k (key, id64) pairs in shared memory.
+// One block per query; (key desc, id asc) bitonic sort of n_shards*k (key, id64) pairs in shared memory.  Shard s
+// holds its scores at cD + s * stride_d and its ids at cI + s * stride_i (elements): two [n_shards, nq, k] arrays, or
+// the packed per-rank blocks [ids | scores] the sharded search all-gathers.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cD, const int64_t* __restrict__ cI,
-                                                         int n_shards, int64_t nq, int k, int metric, int P,
-                                                         float* __restrict__ D, int64_t* __restrict__ I) {
+                                                         int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
+                                                         int k, int metric, int P, float* __restrict__ D,
+                                                         int64_t* __restrict__ I) {
   extern __shared__ uint64_t sm[];
   uint64_t* keys = sm;                 // [P] key in the high word (0 = empty)
   int64_t* ids = (int64_t*)(sm + P);   // [P]
@@ -741,9 +765,9 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     int64_t id = INT64_MAX;
     if (i < total) {
       int s = i / k, j = i % k;
-      int64_t gid = cI[((int64_t)s * nq + q) * k + j];
+      int64_t gid = cI[(int64_t)s * stride_i + q * k + j];
       if (gid >= 0) {
-        float sc = cD[((int64_t)s * nq + q) * k + j];
+        float sc = cD[(int64_t)s * stride_d + q * k + j];
         kk = (uint64_t)score_key(metric == 0 ? sc : -sc) + 1ull;  // +1: keep 0 for "empty"
         id = gid;
       }
@@ -783,16 +807,17 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
 }
 
-int launch_topk_merge(const float* cD, const int64_t* cI, int n_shards, int64_t nq, int k, int metric, float* D,
-                      int64_t* I, cudaStream_t stream) {
+int launch_topk_merge(const float* cD, const int64_t* cI, int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
+                      int k, int metric, float* D, int64_t* I, cudaStream_t stream) {
   if (nq <= 0 || k <= 0) return 0;
   int total = n_shards * k;
   int P = 2;
   while (P < total) P <<= 1;
   size_t smem = (size_t)P * 16;
-  SSS_REQUIRE(smem <= 96 * 1024, "n_shards * k too large for topk_merge_kernel");
-  SSS_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  topk_merge_kernel<<<(unsigned)nq, 256, smem, stream>>>(cD, cI, n_shards, nq, k, metric, P, D, I);
+  SSS_REQUIRE(smem <= 128 * 1024, "sss_topk_merge: n_shards * k must be <= 8192");
+  static SmemAttr attr;
+  if (attr.ensure(topk_merge_kernel, (int)smem)) return 1;
+  topk_merge_kernel<<<(unsigned)nq, 256, smem, stream>>>(cD, cI, stride_d, stride_i, n_shards, nq, k, metric, P, D, I);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

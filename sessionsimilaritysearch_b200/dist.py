@@ -42,9 +42,46 @@ def cuda_merge(cand_D, cand_I, metric=_lib.METRIC_IP):
     return D, I
 
 
+def cuda_merge_packed(gathered, n_shards, nq, k, metric=_lib.METRIC_IP):
+    """sss_topk_merge_packed: `gathered` is the all-gathered uint8 tensor of n_shards packed candidate blocks"""
+    import torch
+    lib = _lib.load()
+    dev = gathered.device.index
+    D = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+    _lib.check(lib.sss_topk_merge_packed(gathered.data_ptr(), n_shards, nq, k, metric, D.data_ptr(), I.data_ptr(), dev,
+                                         _lib.current_stream(dev)))
+    return D, I
+
+
+def pack_candidates(D, I):
+    """host-side restatement of the packed block layout (CPU tests of the sharded logic): uint8 [packed_bytes]"""
+    import torch
+    nq, k = D.shape
+    n = (nq * k * 12 + 15) // 16 * 16
+    out = torch.zeros(n, dtype=torch.uint8)
+    out[:nq * k * 8] = I.contiguous().view(-1).view(torch.uint8)
+    out[nq * k * 8:nq * k * 12] = D.contiguous().view(-1).view(torch.uint8)
+    return out
+
+
+def unpack_candidates(gathered, n_shards, nq, k):
+    """inverse of the packed layout for n_shards blocks laid end to end -> (D [ns, nq, k], I [ns, nq, k])"""
+    import torch
+    blk = (nq * k * 12 + 15) // 16 * 16
+    g = gathered.view(n_shards, blk)
+    I = g[:, :nq * k * 8].contiguous().view(torch.int64).view(n_shards, nq, k)
+    D = g[:, nq * k * 8:nq * k * 12].contiguous().view(torch.float32).view(n_shards, nq, k)
+    return D, I
+
+
 class ShardedIndex:
     """index.search() over a row-sharded database.  `inner` is this rank's shard index (built with
-    id_offset = the shard's first global row / session id)."""
+    id_offset = the shard's first global row / session id).
+
+    CUDA path (NCCL): three calls per search and no eager tensor arithmetic — the shard search emits its candidates
+    as one packed block, ONE all-gather moves the blocks, the merge kernel reads the gathered blocks in place.
+    `merge_fn` (CPU tests over gloo) replaces the CUDA search + merge with host stand-ins on the same layout."""
 
     def __init__(self, inner, world_size=None, rank=None, group=None, merge_fn=None, metric=_lib.METRIC_IP):
         import torch.distributed as dist
@@ -52,8 +89,9 @@ class ShardedIndex:
         self.group = group
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.rank = dist.get_rank(group) if rank is None else rank
-        self.merge_fn = cuda_merge if merge_fn is None else merge_fn
+        self.merge_fn = merge_fn
         self.metric = metric
+        self._gathered = None
 
     @property
     def ntotal(self):
@@ -70,24 +108,26 @@ class ShardedIndex:
         import torch
         import torch.distributed as dist
         host_in = not type(x).__module__.startswith("torch")
-        if host_in and dist.get_backend(self.group) == "nccl":
-            xq = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda(self.inner.device, non_blocking=True)
-        else:
-            xq = x
-        D, I = self.inner.search(xq, k, **kw)
-        if not type(D).__module__.startswith("torch"):
-            D, I = torch.from_numpy(D), torch.from_numpy(I)
-        nq, kk = D.shape
-        # ONE all-gather: ids and score bits packed side by side as int64 [nq, 2k] (16 B per candidate)
-        packed = torch.empty((nq, 2 * kk), dtype=torch.int64, device=D.device)
-        packed[:, :kk] = I
-        packed[:, kk:] = D.contiguous().view(torch.int32).to(torch.int64)
-        gathered = torch.empty((self.world_size * nq, 2 * kk), dtype=torch.int64, device=D.device)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)  # rank-major concatenation
-        gathered = gathered.view(self.world_size, nq, 2 * kk)
-        cI = gathered[..., :kk].contiguous()
-        cD = gathered[..., kk:].to(torch.int32).contiguous().view(torch.float32)
-        Dm, Im = self.merge_fn(cD, cI, self.metric)
-        if host_in and type(Dm).__module__.startswith("torch"):
+        k = int(k)
+        if self.merge_fn is not None:  # host stand-ins (gloo): same packed layout, same single all-gather
+            D, I = self.inner.search(x, k, **kw)
+            if not type(D).__module__.startswith("torch"):
+                D, I = torch.from_numpy(np.ascontiguousarray(D)), torch.from_numpy(np.ascontiguousarray(I))
+            nq = D.shape[0]
+            mine = pack_candidates(D.cpu(), I.cpu())
+            gathered = torch.empty(self.world_size * mine.numel(), dtype=torch.uint8)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            cD, cI = unpack_candidates(gathered, self.world_size, nq, k)
+            Dm, Im = self.merge_fn(cD, cI, self.metric)
+            if host_in and type(Dm).__module__.startswith("torch"):
+                return Dm.numpy(), Im.numpy()
+            return Dm, Im
+        mine = self.inner.search_packed(x, k, **kw)
+        nq = x.shape[0]
+        if self._gathered is None or self._gathered.numel() != self.world_size * mine.numel():
+            self._gathered = torch.empty(self.world_size * mine.numel(), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(self._gathered, mine, group=self.group)  # rank-major concatenation
+        Dm, Im = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
+        if host_in:
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im

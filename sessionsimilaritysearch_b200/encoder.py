@@ -80,9 +80,44 @@ class SessionEncoder:
     def to(self, device):
         return self
 
+    def _batch(self, data, xq, xp):
+        """the sss_graph_batch_t of a SessionBatch / PyG batch (+ the tensors that must outlive the call)"""
+        dev = torch.device("cuda", self.device)
+        ei = data.edge_index_dict
+        qp, pq, pp = _i64(ei[EDGE_QP], dev), _i64(ei[EDGE_PQ], dev), _i64(ei[EDGE_PP], dev)
+        qb, pb = _i64(data["query"].batch, dev), _i64(data["product"].batch, dev)
+        qpos, ppos = _i64(data["query"].pos_emb_id, dev), _i64(data["product"].pos_emb_id, dev)
+        cnt = _i64(data["product"].cnt, dev)
+        n_graphs = int(max(int(qb.max()), int(pb.max()))) + 1
+        rows = [qp[0].contiguous(), qp[1].contiguous(), pq[0].contiguous(), pq[1].contiguous(), pp[0].contiguous(),
+                pp[1].contiguous()]
+        keep = [xq, xp, qb, pb, qpos, ppos, cnt] + rows
+        b = _lib.GraphBatch(n_graphs, qb.shape[0], pb.shape[0], ppos.shape[0],
+                            xq.data_ptr() if xq is not None else None, xp.data_ptr() if xp is not None else None,
+                            qb.data_ptr(), pb.data_ptr(), qpos.data_ptr(), cnt.data_ptr(), ppos.data_ptr(),
+                            qp.shape[1], rows[0].data_ptr(), rows[1].data_ptr(),
+                            pq.shape[1], rows[2].data_ptr(), rows[3].data_ptr(),
+                            pp.shape[1], rows[4].data_ptr(), rows[5].data_ptr())
+        return b, keep, n_graphs
+
+    def _run(self, b, out=None, zq=None, zp=None, run_gnn=True, run_pooling=True):
+        dev = torch.device("cuda", self.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        io = _lib.EncoderIO(out.data_ptr() if out is not None else None, zq.data_ptr() if zq is not None else None,
+                            zp.data_ptr() if zp is not None else None, int(run_gnn), int(run_pooling), flag.data_ptr())
+        check(self._lib.sss_encoder_forward_ex(self._h, ctypes.byref(b), ctypes.byref(io),
+                                               _lib.current_stream(self.device)))
+        if int(flag.item()) != 0:             # the reference's isnan asserts (model/model.py:301-314)
+            raise RuntimeError("nan in embedding[query]")
+
+    @property
+    def node_dim(self):
+        return self.in_dim + self.n_layers * self.hidden
+
     def __call__(self, data, query_node_mask=None, product_node_mask=None, get_node=False, get_token=False):
-        if get_node or get_token:
-            raise NotImplementedError("node / token level outputs are training-only paths of the reference")
+        """encoder(data, ...) of model/model.py:279-351.  get_node=True also returns the node embeddings
+        {'query': [N_q, 3168], 'product': [N_p, 3168]}; get_token=True returns the reference's (empty)
+        session_level_token_emb dict — the block that would fill it is commented out there (model/model.py:321-332)."""
         dev = torch.device("cuda", self.device)
         xq = _f32(data["query"].x, dev)
         xp = _f32(data["product"].input_ids, dev)
@@ -90,26 +125,96 @@ class SessionEncoder:
             xq = xq * query_node_mask.to(dev).view(-1, 1)
         if product_node_mask is not None:
             xp = xp * product_node_mask.to(dev).view(-1, 1)
-        ei = data.edge_index_dict
-        qp, pq, pp = _i64(ei[EDGE_QP], dev), _i64(ei[EDGE_PQ], dev), _i64(ei[EDGE_PP], dev)
-        qb, pb = _i64(data["query"].batch, dev), _i64(data["product"].batch, dev)
-        qpos, ppos = _i64(data["query"].pos_emb_id, dev), _i64(data["product"].pos_emb_id, dev)
-        cnt = _i64(data["product"].cnt, dev)
-        n_graphs = int(max(int(qb.max()), int(pb.max()))) + 1
-        keep = [xq, xp, qp, pq, pp, qb, pb, qpos, ppos, cnt]
-        b = _lib.GraphBatch(n_graphs, xq.shape[0], xp.shape[0], ppos.shape[0], xq.data_ptr(), xp.data_ptr(),
-                            qb.data_ptr(), pb.data_ptr(), qpos.data_ptr(), cnt.data_ptr(), ppos.data_ptr(),
-                            qp.shape[1], qp[0].contiguous().data_ptr(), qp[1].contiguous().data_ptr(),
-                            pq.shape[1], pq[0].contiguous().data_ptr(), pq[1].contiguous().data_ptr(),
-                            pp.shape[1], pp[0].contiguous().data_ptr(), pp[1].contiguous().data_ptr())
+        b, keep, n_graphs = self._batch(data, xq, xp)
         out = torch.empty((n_graphs, self.out_dim), dtype=torch.float32, device=dev)
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(self._lib.sss_encoder_forward(self._h, ctypes.byref(b), out.data_ptr(), flag.data_ptr(),
-                                            _lib.current_stream(self.device)))
+        zq = zp = None
+        if get_node:
+            zq = torch.empty((xq.shape[0], self.node_dim), dtype=torch.float32, device=dev)
+            zp = torch.empty((xp.shape[0], self.node_dim), dtype=torch.float32, device=dev)
+        self._run(b, out, zq, zp)
         del keep
-        if int(flag.item()) != 0:             # the reference's isnan asserts (model/model.py:301-314)
-            raise RuntimeError("nan in embedding[query]")
+        if not get_node and not get_token:
+            return out
+        if get_node and not get_token:
+            return out, {"query": zq, "product": zp}
+        if get_token and not get_node:
+            return out, {}
+        return out, {"query": zq, "product": zp}, {}
+
+    def gnn(self, x_dict, edge_index_dict, edge_weight_dict=None, add_input_feat=True, data=None):
+        """gnn(x_dict, edge_index_dict, edge_weight_dict=None, add_input_feat=True) of model/gnn.py:64-81: the three
+        HeteroConv layers; returns {'query': [N_q, in + 3 * hidden], 'product': ...} (without the input block when
+        add_input_feat is False)."""
+        if edge_weight_dict is not None:
+            raise NotImplementedError("the reference never passes edge weights on this path (model/model.py:317); "
+                                      "PyG 2.0.4's GATConv would take them as its `size` argument")
+        dev = torch.device("cuda", self.device)
+        xq, xp = _f32(x_dict["query"], dev), _f32(x_dict["product"], dev)
+        nq, np_ = xq.shape[0], xp.shape[0]
+        z64 = torch.zeros(1, dtype=torch.int64, device=dev)
+        rows = []
+        for key in (EDGE_QP, EDGE_PQ, EDGE_PP):
+            e = _i64(edge_index_dict[key], dev)
+            rows += [e[0].contiguous(), e[1].contiguous()]
+        # the GNN stage reads neither batch vectors nor positions: one graph, placeholders of the right length
+        qb = torch.zeros(nq, dtype=torch.int64, device=dev)
+        pb = torch.zeros(np_, dtype=torch.int64, device=dev)
+        cnt = torch.ones(np_, dtype=torch.int64, device=dev)
+        b = _lib.GraphBatch(1, nq, np_, np_, xq.data_ptr(), xp.data_ptr(), qb.data_ptr(), pb.data_ptr(), qb.data_ptr(),
+                            cnt.data_ptr(), pb.data_ptr(),
+                            rows[0].shape[0], rows[0].data_ptr(), rows[1].data_ptr(),
+                            rows[2].shape[0], rows[2].data_ptr(), rows[3].data_ptr(),
+                            rows[4].shape[0], rows[4].data_ptr(), rows[5].data_ptr())
+        zq = torch.empty((nq, self.node_dim), dtype=torch.float32, device=dev)
+        zp = torch.empty((np_, self.node_dim), dtype=torch.float32, device=dev)
+        self._run(b, None, zq, zp, run_gnn=True, run_pooling=False)
+        del z64
+        if add_input_feat:
+            return {"query": zq, "product": zp}
+        return {"query": zq[:, self.in_dim:].contiguous(), "product": zp[:, self.in_dim:].contiguous()}
+
+    def pooling(self, node_emb_dict, data):
+        """pooling(input_emb, data) of model/gnn.py:193-217: node embeddings [N, in + 3 * hidden] -> [B, out_dim]"""
+        dev = torch.device("cuda", self.device)
+        zq, zp = _f32(node_emb_dict["query"], dev), _f32(node_emb_dict["product"], dev)
+        if zq.shape[1] != self.node_dim or zp.shape[1] != self.node_dim:
+            raise ValueError("pooling expects node embeddings of width %d" % self.node_dim)
+        b, keep, n_graphs = self._batch(data, None, None)
+        out = torch.empty((n_graphs, self.out_dim), dtype=torch.float32, device=dev)
+        self._run(b, out, zq, zp, run_gnn=False, run_pooling=True)
+        del keep
         return out
+
+
+def masked_mean_pool(token_emb, attention_mask, get_token=False):
+    """The tail of PretrainedQAEAEncoder.__call__ (model/NodeEmbedding.py:112-125, lin=None): the transformer's
+    last_hidden_state [N, L, H] and the tokenizer's attention_mask [N, L] -> sum_t tok * mask / sum_t mask, detached;
+    with get_token=True also the token embeddings, as the reference returns them."""
+    lib = _lib.load()
+    if token_emb.device.type != "cuda":
+        raise RuntimeError("masked_mean_pool runs on a CUDA device (no CPU fallback)")
+    dev = token_emb.device
+    tok = token_emb.detach().to(torch.float32).contiguous()
+    mask = attention_mask.to(device=dev, dtype=torch.int64).contiguous()
+    n, L, H = tok.shape
+    out = torch.empty((n, H), dtype=torch.float32, device=dev)
+    check(lib.sss_masked_mean(tok.data_ptr(), mask.data_ptr(), n, L, H, out.data_ptr(), dev.index,
+                              _lib.current_stream(dev.index)))
+    return (out, token_emb) if get_token else out
+
+
+def cosine_matrix(a, b):
+    """F.normalize(a) @ F.normalize(b).T (fine_tune_ours.py:133,480,494,613,626) on CUDA tensors [na, d], [nb, d]"""
+    lib = _lib.load()
+    if a.device.type != "cuda":
+        raise RuntimeError("cosine_matrix runs on a CUDA device (no CPU fallback)")
+    dev = a.device
+    a = a.detach().to(torch.float32).contiguous()
+    b = b.detach().to(device=dev, dtype=torch.float32).contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=dev)
+    check(lib.sss_cosine_matrix(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], a.shape[1], out.data_ptr(),
+                                dev.index, _lib.current_stream(dev.index)))
+    return out
 
 
 class BinarizeHead:

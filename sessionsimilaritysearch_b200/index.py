@@ -78,11 +78,12 @@ class _FlatIndex:
         search() then returns session ids scored by the max (or sum) over their rows."""
         if reduce not in REDUCES:
             raise ValueError("reduce must be one of None, 'max', 'sum'")
+        st = _lib.current_stream(self.device)
         if REDUCES[reduce] == 0:
-            check(self._lib.sss_index_set_segments(self._h, None, 0, 0))
+            check(self._lib.sss_index_set_segments(self._h, None, 0, 0, st))
             return
         so = np.ascontiguousarray(np.asarray(seg_off.cpu() if _is_torch(seg_off) else seg_off), dtype=np.int64)
-        check(self._lib.sss_index_set_segments(self._h, so.ctypes.data, so.shape[0] - 1, REDUCES[reduce]))
+        check(self._lib.sss_index_set_segments(self._h, so.ctypes.data, so.shape[0] - 1, REDUCES[reduce], st))
 
     def search(self, x, k, mode=None):
         """D, I = index.search(x, K): D float32 [nq, K] best first, I int64 [nq, K]; ties -> smaller id."""
@@ -105,8 +106,27 @@ class _FlatIndex:
                                          _lib.current_stream(self.device)))
         return D, I
 
+    def search_packed(self, x, k, mode=None):
+        """The sharded path's form of search(): one uint8 CUDA tensor holding this shard's candidates as
+        [ids int64 nq*k | scores fp32 nq*k] (sss_packed_bytes), ready to be all-gathered as it is."""
+        import torch
+        m = MODES[self.mode if mode is None else mode]
+        k = int(k)
+        dev = torch.device("cuda", self.device)
+        if _is_torch(x):
+            x = _f32_dev(x, self.d, self.device)
+            ptr, on_dev, nq = x.data_ptr(), 1, x.shape[0]
+        else:
+            x = _f32_host(x, self.d)
+            ptr, on_dev, nq = x.ctypes.data, 0, x.shape[0]
+        out = torch.empty(int(self._lib.sss_packed_bytes(nq, k)), dtype=torch.uint8, device=dev)
+        check(self._lib.sss_index_search_packed(self._h, ptr, nq, k, m, on_dev, out.data_ptr(),
+                                                _lib.current_stream(self.device)))
+        return out
+
     def set_profiling(self, on=True):
-        """time every scan-kernel launch with CUDA events on the launching stream (bench.py roofline)"""
+        """time every scan-kernel launch with CUDA events on the launching stream (bench.py roofline); a profiled
+        search runs as plain launches instead of replaying its captured CUDA graph"""
         check(self._lib.sss_index_set_profiling(self._h, int(bool(on))))
 
     def stats(self):
@@ -115,8 +135,7 @@ class _FlatIndex:
                 "scan_ns": int(st(self._h, 3)), "scan_launches": int(st(self._h, 4)),
                 "refine_candidates": int(st(self._h, 5)), "refine_rescored": int(st(self._h, 6)),
                 "refine_sessions": int(st(self._h, 7)), "refine_calls": int(st(self._h, 8)),
-                "refine_phase_cycles": [int(st(self._h, 9 + p)) for p in range(7)],
-                "overflow_reason": int(st(self._h, 24)),
+                "overflow_reason": int(st(self._h, 24)), "graph": int(st(self._h, 26)),
                 "scan_variant": ("fp32", "ss", "ts", "2cta", "kloop")[int(st(self._h, 25))]}
 
 

@@ -20,6 +20,7 @@ class ItemLists:
             flat.append(x)
         dev = torch.device("cuda", self.device)
         self.n = len(lens)
+        self.max_len = int(max(lens)) if lens else 0
         self.item_off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
         self.items = torch.from_numpy(np.concatenate(flat) if flat else np.zeros(0, np.int64)).to(dev)
 
@@ -34,7 +35,8 @@ def item_vote(D, I, lists, K):
     out_i = torch.empty((nq, K), dtype=torch.int64, device=dev)
     out_w = torch.empty((nq, K), dtype=torch.float32, device=dev)
     check(lib.sss_item_vote(Dt.data_ptr(), It.data_ptr(), nq, s, lists.item_off.data_ptr(), lists.items.data_ptr(),
-                            lists.n, K, out_i.data_ptr(), out_w.data_ptr(), lists.device, _lib.current_stream(lists.device)))
+                            lists.n, K, s * lists.max_len, out_i.data_ptr(), out_w.data_ptr(), lists.device,
+                            _lib.current_stream(lists.device)))
     return out_i, out_w
 
 
@@ -42,7 +44,8 @@ _cache = {}
 
 
 def get_prediction_by_knn(emb, index, dataset, sample_size, K):
-    """same signature and result as the reference: ids of the K items with the largest summed neighbour similarity"""
+    """same signature and result as the reference: ids of the K items with the largest summed neighbour similarity
+    (float64 sums in arrival order, equal sums in order of first arrival — pinned by tests/golden/vote_golden.npz)"""
     key = id(dataset)
     if key not in _cache:
         _cache.clear()

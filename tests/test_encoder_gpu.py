@@ -185,6 +185,8 @@ def test_item_vote_and_get_prediction_by_knn(oracle):
     I = np.stack([rng.permutation(n_sess)[:60] for _ in range(9)]).astype(np.int64)
     I[0, 50:] = -1                       # padded neighbours are skipped
     D = np.sort(rng.random((9, 60)).astype(np.float32), axis=1)[:, ::-1].copy()
+    # (reference semantics — float64 sums, ties in arrival order — are pinned in test_metrics_gpu.py against the
+    # fixture the reference's own function produced)
     oi, ow = sss.item_vote(D, I, lists, 20)
     ei, ew = oracle.item_vote(D, I, item_off, items, 20)
     assert np.array_equal(oi.cpu().numpy(), ei)

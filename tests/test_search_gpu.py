@@ -2,7 +2,7 @@
 CPU oracle (oracle/search_oracle.c, O2) on the same seeded inputs.
 
 Bars (BASELINE.json north_star): fp32 and exact modes bit-exact ids AND scores vs O2 (ties by id);
-bf16 mode |score - O1| <= 1e-3 and recall@k >= 0.999.
+bf16 mode |score - O1| <= 1e-3 and recall@k >= 0.999 (asserted at exactly those values below).
 """
 import numpy as np
 import pytest
@@ -69,31 +69,30 @@ def test_flat_ip_raw_unnormalised(sss, oracle, mode):
 
 
 def test_bf16_bar_recall_and_score_tolerance(sss, oracle):
-    """north_star bf16 bar: scores within 1e-3 absolute of the reference path (O1) and recall@k >= 0.999.
-    The default mode ("exact": tcgen05 bf16 scan + fixed-order fp32 rescoring of the survivors) must meet it;
-    the raw tensor-core scores (mode "bf16", no fp32 copy consulted) are within the score tolerance but lose
-    a few boundary neighbours to bf16 rounding of the database, which is recorded here, not hidden."""
+    """north_star bf16 bar: scores within 1e-3 absolute of the reference path (O1) and recall@k >= 0.999 — for BOTH
+    tensor-core modes.  "exact" filters with a rigorous slack, "bf16" with a statistical one (4 sigma of the bf16
+    rounding noise); both re-score what passes in fixed-order fp32."""
     db = make_clustered(200000, 128, 5)
     q = make_clustered(64, 128, 6)
     ix = sss.build_index(db, 'cos')
     qn = sss.normalize(q)
     Do, Io = oracle.search_blas(oracle.normalize_util_numpy(db), oracle.normalize_util_numpy(q), 100)  # O1
+    D2, I2 = oracle.search_flat(oracle.normalize(db, 1), oracle.normalize(q, 1), 100)                  # O2
 
-    def recall(I):
-        return np.mean([len(set(I[r]) & set(Io[r])) / 100.0 for r in range(q.shape[0])])
+    def recall(I, ref):
+        return np.mean([len(set(I[r]) & set(ref[r])) / 100.0 for r in range(q.shape[0])])
 
-    D, I = ix.search(qn, 100, mode="exact")
-    assert recall(I) >= 0.999, recall(I)
-    assert np.max(np.abs(D - Do)) <= 1e-3
-    Dr, Ir = ix.search(qn, 100, mode="bf16")
-    assert np.max(np.abs(Dr - Do)) <= 1e-3          # rank-wise scores
-    assert recall(Ir) >= 0.98, recall(Ir)            # measured 0.992-0.997 on this generator
-    assert np.all(np.diff(Dr, axis=1) <= 0)
-    common = [dict(zip(Io[r], Do[r])) for r in range(q.shape[0])]
-    for r in range(q.shape[0]):
-        for i, s in zip(Ir[r], Dr[r]):
-            if i in common[r]:
-                assert abs(float(s) - float(common[r][i])) <= 1e-3
+    for mode in ("exact", "bf16"):
+        D, I = ix.search(qn, 100, mode=mode)
+        assert recall(I, Io) >= 0.999, (mode, recall(I, Io))
+        assert recall(I, I2) >= 0.999, (mode, recall(I, I2))
+        assert np.max(np.abs(D - Do)) <= 1e-3, mode     # rank-wise scores against the BLAS path
+        assert np.all(np.diff(D, axis=1) <= 0)
+        common = [dict(zip(I2[r], D2[r])) for r in range(q.shape[0])]
+        for r in range(q.shape[0]):                       # a returned row carries its fixed-order fp32 score
+            for i, sc in zip(I[r], D[r]):
+                if i in common[r]:
+                    assert np.float32(sc) == np.float32(common[r][i])
 
 
 @pytest.mark.parametrize("mode", ["fp32", "exact"])
@@ -202,7 +201,7 @@ def test_million_rows_exact_equals_fp32_and_oracle_sample(sss, oracle):
     _assert_exact(D[sub], I[sub], Do, Io)
     Db, Ib = ix.search(qn, 100, mode="bf16")
     recall = np.mean([len(set(Ib[r]) & set(I[r])) / 100.0 for r in range(1000)])
-    assert recall >= 0.98 and np.max(np.abs(Db - D)) <= 2e-3, recall  # raw bf16: tail of 1e5 scores reaches ~1.1e-3
+    assert recall >= 0.999 and np.max(np.abs(Db - D)) <= 1e-3, recall
 
 
 @pytest.mark.parametrize("d,n,nq", [(256, 300000, 300), (1600, 270000, 130)])
@@ -228,7 +227,7 @@ def test_wide_rows_take_the_kloop_tensor_path(sss, oracle, d, n, nq):
     _assert_exact(Ds, Is, Do, Io)
     Db, Ib = ix.search(qn, 50, mode="bf16")
     recall = np.mean([len(set(Ib[r]) & set(I[r])) / 50.0 for r in range(nq)])
-    assert recall >= 0.97 and np.max(np.abs(Db - D)) <= 3e-3, recall
+    assert recall >= 0.999 and np.max(np.abs(Db - D)) <= 1e-3, recall
 
 
 @pytest.mark.parametrize("case", ["ties", "ties_sessions", "long_sessions", "k256", "k300"])
@@ -290,7 +289,7 @@ def test_full_record_subregion_retries_with_more_room_not_the_safe_schedule(sss,
     qn = sss.normalize(q)
     D, I = ix.search(qn, 100)
     st = ix.stats()
-    assert st["scan_variant"] == "2cta" and st["reruns"] == 1 and st["overflow_reason"] == 1 and st["waves"] <= 8, st
+    assert st["scan_variant"] == "2cta" and st["reruns"] == 1 and st["overflow_reason"] == 1 and st["waves"] <= 16, st
     D2, I2 = ix.search(qn, 100, mode="fp32")
     _assert_exact(D, I, D2, I2)
     assert np.all((I[5] // 256 == 600) | (I[5] // 256 == 674) | (I[5] // 256 == 748))
@@ -323,9 +322,9 @@ def test_l2_on_the_tensor_path(sss, oracle, d, n, nq, seg_mean):
     sub = np.arange(0, nq, max(1, nq // 3))[:3]
     Do, Io = oracle.search_flat(db, q[sub], 50, metric=oracle.METRIC_L2, seg_off=seg, reduce=1 if seg is not None else 0)
     _assert_exact(D[sub], I[sub], Do, Io)
-    Db, Ib = ix.search(q, 50, mode="bf16")
+    Db, Ib = ix.search(q, 50, mode="bf16")   # (L2 keeps the rigorous slack in both tensor-core modes)
     recall = np.mean([len(set(Ib[r]) & set(I[r])) / 50.0 for r in range(nq)])
-    assert recall >= 0.95 and np.max(np.abs(Db - D) / (1.0 + D)) <= 2e-2, recall
+    assert recall >= 0.999 and np.max(np.abs(Db - D)) <= 1e-3 * (1.0 + float(D.max())), recall
 
 
 def test_torch_device_tensors(sss, oracle):
@@ -362,3 +361,92 @@ def test_binary_hamming(sss, oracle):
     Do, Io = oracle.search_hamming(codes, qcodes, 100)
     assert D.dtype == np.int32 and np.array_equal(D, Do) and np.array_equal(I, Io)
     assert ix.ntotal == 40000
+
+
+def test_headline_config_10m_rows_against_the_oracle(sss, oracle):
+    """BASELINE configs[2] at FULL size: 10M subsession rows x 128, sessions of 1 + Poisson(7) rows, fused
+    per-session max, top-100 sessions.  exact mode against the CPU oracle O2 on 16 sampled queries (ids and scores
+    bit for bit) and against the bit-faithful fp32 mode on all 1000; bf16 mode at the north-star bar."""
+    import torch
+    n, d, nq, k = 10_000_000, 128, 1000, 100
+    seg = make_segments(n, 71)
+    lens = torch.from_numpy(np.diff(seg)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(72)
+    ix = sss.IndexFlatIP(d, mode="exact")
+    host = np.empty((n, d), dtype=np.float32)
+    bases = []
+    s0 = 0
+    for c0 in range(0, len(lens), 131072):
+        l = lens[c0:c0 + 131072]
+        base = torch.randn((l.numel(), d), generator=g, device="cuda")
+        rows = torch.repeat_interleave(base, l, dim=0)
+        rows += 0.3 * torch.randn(rows.shape, generator=g, device="cuda")
+        ix.add(rows, norm=sss.NORM_UTIL)
+        host[s0:s0 + rows.shape[0]] = rows.cpu().numpy()
+        s0 += rows.shape[0]
+        bases.append(base[::997].clone())
+    assert s0 == n and ix.ntotal == n
+    ix.set_segments(seg, "max")
+    pool = torch.cat(bases)
+    pick = torch.randint(0, pool.shape[0], (nq,), generator=g, device="cuda")   # targets spread over the whole database
+    q = sss.normalize(pool[pick] + 0.3 * torch.randn((nq, d), generator=g, device="cuda"))
+    D, I = ix.search(q, k)
+    st = ix.stats()
+    assert st["reruns"] == 0 and st["scan_variant"] == "2cta", st
+    D1, I1 = ix.search(q, k)                       # second call replays the captured graph
+    assert ix.stats()["graph"] == 1 and torch.equal(I, I1) and torch.equal(D, D1)
+    D2, I2 = ix.search(q, k, mode="fp32")
+    assert torch.equal(I, I2) and torch.equal(D, D2)
+    sub = np.arange(0, nq, nq // 16)[:16]
+    q_np = q.cpu().numpy()
+    Do, Io = oracle.search_flat(oracle.normalize(host, oracle.NORM_UTIL), q_np[sub], k, seg_off=seg, reduce=oracle.REDUCE_MAX)
+    _assert_exact(D.cpu().numpy()[sub], I.cpu().numpy()[sub], Do, Io)
+    Db, Ib = ix.search(q, k, mode="bf16")
+    Ie, Ibn = I.cpu().numpy(), Ib.cpu().numpy()
+    recall = np.mean([len(set(Ibn[r]) & set(Ie[r])) / float(k) for r in range(nq)])
+    assert recall >= 0.999 and float((Db - D).abs().max()) <= 1e-3, recall
+    # host buffers in / out: the same answer through the e2e form of the call
+    Dh, Ih = ix.search(q_np, k)
+    assert np.array_equal(Ih, Ie) and np.array_equal(Dh, D.cpu().numpy())
+
+
+def test_two_handles_on_two_devices_in_one_process(sss, oracle):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: an index on cuda:1 built after one on
+    cuda:0 must launch (scan, refine, merge) with its own opt-in.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    seg = make_segments(300000, 81)
+    db = make_session_rows(seg, 128, 82)
+    q = make_iid(200, 128, 83)
+    Do, Io = oracle.search_flat(oracle.normalize(db, 1), oracle.normalize(q, 1), 50, seg_off=seg, reduce=1)
+    for dev in (0, 1, 0):
+        ix = sss.build_index(db, 'cos', device=dev, mode="exact")
+        ix.set_segments(seg, "max")
+        D, I = ix.search(sss.normalize(q, device=dev), 50)
+        _assert_exact(D, I, Do, Io)
+        with torch.cuda.device(dev):
+            Dt, It = ix.search(torch.from_numpy(oracle.normalize(q, 1)).to("cuda:%d" % dev), 50)
+        _assert_exact(Dt.cpu().numpy(), It.cpu().numpy(), Do, Io)
+
+
+def test_graph_replay_follows_new_buffers_and_index_changes(sss, oracle):
+    """A search is replayed from a CUDA graph captured on its first call; the query / output pointers are re-bound on
+    every replay and add() / set_segments() drop the captured graphs."""
+    import torch
+    db = make_iid(300000, 128, 91)
+    ix = sss.build_index(db[:280000], 'cos', mode="exact")
+    dbn = oracle.normalize(db, 1)
+    for i in range(3):
+        q = oracle.normalize(make_iid(256, 128, 92 + i), 1)
+        qd = torch.from_numpy(q).cuda() if i != 1 else q          # fresh buffers each time, host and device forms
+        D, I = ix.search(qd, 20)
+        D, I = (D.cpu().numpy(), I.cpu().numpy()) if i != 1 else (D, I)
+        Do, Io = oracle.search_flat(dbn[:280000], q[::32], 20)
+        _assert_exact(D[::32], I[::32], Do, Io)
+        assert ix.stats()["graph"] == 1
+    ix.add(db[280000:], norm=sss.NORM_UTIL)
+    q = oracle.normalize(make_iid(256, 128, 99), 1)
+    D, I = ix.search(q, 20)
+    Do, Io = oracle.search_flat(dbn, q[::32], 20)
+    _assert_exact(D[::32], I[::32], Do, Io)
