@@ -35,7 +35,8 @@
 
 /* util_amazon_filtered.py:28-31 / fine_tune_ours.py:38-40 / F.normalize, with a fixed summation order */
 void o_normalize(const float* in, float* out, int64_t n, int d, int mode) {
-  for (int64_t i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) { /* rows are independent; the order INSIDE a row is what is fixed */
     const float* x = in + i * (int64_t)d;
     float* y = out + i * (int64_t)d;
     if (mode == O_NORM_NONE) {

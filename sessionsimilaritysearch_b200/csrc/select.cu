@@ -636,14 +636,15 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
 // sessions/rows whose scores are >= T, the smallest of those maxima.  So the k-th best exact session score is >= T - margin and a row
 // can only matter if its tensor-core score is >= T - 2 * margin: thr = the float just below that.
 // One block = 8 consecutive queries: the chunk maxima are stored [chunk][query], so 8 threads read one full 32-byte
-// sector per chunk (a block per query read 4 of every 32 bytes it pulled: 128 MB of L2 traffic per 1000 queries);
-// then warp w radix-selects (4 x 8 bits, warp-synchronous) the need-th largest key of query w.
+// sector per chunk (a block per query read 4 of every 32 bytes it pulled: 128 MB of L2 traffic per 1000 queries).
+// Warp w then finds the need-th largest key of query w by a bitwise binary search from the top bit down — 32 counting
+// passes over its 4096 keys in shared memory, no atomics (a radix select's histogram serialises here: the maxima of
+// one query share their leading bits, so a whole warp hits two or three bins).
 constexpr int kBootQ = 8;
 __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq,
                                                             int64_t nq_pad, int k, int chunk_gap, float slack_mult,
                                                             SelectState st) {
   extern __shared__ uint32_t bs_keys[];  // [kBootQ][n_chunks + 8] (row pitch keeps the transposing stores conflict free)
-  __shared__ uint32_t hist_all[kBootQ][256];
   const int pitch = n_chunks + 8;
   const int64_t q0 = (int64_t)blockIdx.x * kBootQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -659,49 +660,13 @@ __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restr
   const int64_t q = q0 + warp;
   if (q >= nq) return;
   const uint32_t* keys = bs_keys + warp * pitch;
-  uint32_t* hist = hist_all[warp];
-  uint32_t prefix = 0u, mask = 0u;
-  int want = need;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int b = lane; b < 256; b += 32) hist[b] = 0u;
-    __syncwarp();
-    for (int i = lane; i < n_chunks; i += 32) {
-      const uint32_t key = keys[i];
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
-    }
-    __syncwarp();
-    // lane l owns bins [8l, 8l + 8); find the bin where the count from the top reaches `want`
-    int mine = 0;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) mine += (int)hist[lane * 8 + b];
-    int above = mine;  // inclusive suffix sum over lanes >= l
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_down_sync(0xffffffffu, above, o);
-      if (lane + o < 32) above += t;
-    }
-    const int strictly_above = above - mine;  // counts in higher lanes
-    const bool owner = strictly_above < want && above >= want;
-    int bin = 0, acc_above = 0;
-    if (owner) {
-      int acc = strictly_above;
-      for (int b = 7; b >= 0; --b) {
-        const int c = (int)hist[lane * 8 + b];
-        if (acc + c >= want) {
-          bin = lane * 8 + b;
-          acc_above = acc;
-          break;
-        }
-        acc += c;
-      }
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, owner);
-    const int src = __ffs(bal) - 1;  // exactly one owner: the counts from the top pass `want` in one lane
-    bin = __shfl_sync(0xffffffffu, bin, src);
-    acc_above = __shfl_sync(0xffffffffu, acc_above, src);
-    want -= acc_above;
-    prefix |= (uint32_t)bin << shift;
-    mask |= 0xFFu << shift;
-    __syncwarp();
+  uint32_t prefix = 0u;  // largest value v with count(keys >= v) >= need, built bit by bit = the need-th largest key
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int cnt = 0;
+    for (int i = lane; i < n_chunks; i += 32) cnt += keys[i] >= cand ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt >= need) prefix = cand;
   }
   if (lane == 0) st.thr[q] = nextafterf(key_score(prefix) - slack_mult * st.margin[q], -INFINITY);
 }
