@@ -137,11 +137,18 @@ int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k,
 
 /* ---- binary index (replaces faiss.IndexBinaryFlat, fine_tune_ours.py:839-843,871-876) ------------ */
 
-/* nbits must be a multiple of 8; codes are uint8 [n, nbits/8] as produced by np.packbits(axis=1). */
+/* nbits must be a multiple of 8, <= 512; codes are uint8 [n, nbits/8] as produced by np.packbits(axis=1).
+ * Searches of more than 16 queries over codes of up to 256 bits (the reference hashes to 250) run on the tensor
+ * cores: the index also keeps every code as +-1.0 in E4M3 (one byte per bit), <a, b> = nbits - 2 * hamming is exact
+ * in the fp32 accumulators, and the fused scan + streaming top-k of the float index applies unchanged (bootstrap
+ * thresholds, waves, graph replay).  Fewer queries, or longer codes, take a popcount scan over the packed codes. */
 int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset);
 int sss_binary_destroy(sss_binary_index_t* ix);
 int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream);
 int64_t sss_binary_ntotal(const sss_binary_index_t* ix);
+/* the counters of sss_index_stat / the switch of sss_index_set_profiling, for a binary index */
+int64_t sss_binary_stat(const sss_binary_index_t* ix, int what);
+int sss_binary_set_profiling(sss_binary_index_t* ix, int on);
 /* D: int32 [nq, k] Hamming distances ascending, I: int64 [nq, k]; ties: smaller id first. */
 int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64_t nq, int k, int q_on_device,
                       int32_t* D, int64_t* I, int out_on_device, void* stream);

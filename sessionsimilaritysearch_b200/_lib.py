@@ -75,6 +75,8 @@ SIGNATURES = {
     "sss_binary_destroy": (c_int, [c_vp]),
     "sss_binary_add": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "sss_binary_ntotal": (c_i64, [c_vp]),
+    "sss_binary_stat": (c_i64, [c_vp, c_int]),
+    "sss_binary_set_profiling": (c_int, [c_vp, c_int]),
     "sss_binary_search": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "sss_pack_sign_bits": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "sss_item_vote": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp]),

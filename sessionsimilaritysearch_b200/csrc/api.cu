@@ -253,6 +253,11 @@ struct sss_index {
   int64_t scan_launches = 0;
   unsigned long long* dbg = nullptr;  // device [12], see RefineArgs::debug
   unsigned long long dbg_host[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // Binary flavour (sss_binary_index wraps one of these): rows.f32 holds the PACKED codes (pitch = 4 * d bytes per
+  // row), rows.bf16 their +-1 E4M3 expansion (2 * d_pad bytes per row); scores are integers, nothing is re-scored.
+  bool binary = false;
+  int b_nbits = 0, b_nbytes = 0;
+  int64_t q_row_bytes() const { return binary ? b_nbytes : (int64_t)d * 4; }
   void drop_graphs() {
     for (auto& g : graphs) g.destroy();
     graphs.clear();
@@ -509,6 +514,7 @@ static int replan(sss_index* ix, SearchCtx& c) {
   if (plan_scan_bf16(ix->d_pad, c.nq_pad, ix->num_sms, 8, &c.plan, ix->rec_boost,
                      ix->d + (ix->metric == SSS_METRIC_L2 ? 2 : 0), ix->tune.variant))
     return 1;
+  c.plan.fp8 = ix->binary;
   return ix->ws.ensure_records(2 * c.plan.n_regions, c.plan.rec_cap);
 }
 
@@ -525,9 +531,14 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
   SelectState state = ws.state();
   state.cap = c.cap;
   const int slack = !tensor ? 0 : c.mode == SSS_MODE_EXACT ? 1 : 2;
-  if (launch_prep_queries(q_in, c.nq, c.nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr, slack, rs.maxnorm2, state,
-                          st, c.l2_tensor ? 1 : 0, ws.q_keep))
+  if (ix->binary) {
+    if (launch_prep_binary((const uint8_t*)q_in, c.nq, c.nq_pad, ix->b_nbytes, ix->d_pad * 2,
+                           tensor ? (uint8_t*)ws.q_bf16 : nullptr, tensor ? nullptr : (uint8_t*)ws.q_keep, ix->d * 4, state, st))
+      return 1;
+  } else if (launch_prep_queries(q_in, c.nq, c.nq_pad, ix->d, ix->d_pad, tensor ? ws.q_bf16 : nullptr, slack, rs.maxnorm2,
+                                 state, st, c.l2_tensor ? 1 : 0, ws.q_keep)) {
     return 1;
+  }
   SSS_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, sizeof(int), st));
   c.kernels += 1;
   RefineArgs ra;
@@ -598,6 +609,8 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
       if (launch_scan_bf16(plan, c.tmap_q, c.tmap_db, ws.q_bf16, begin, end, state, rec_buf, cnt_buf, ws.flags + 1,
                            nullptr, st))
         return 1;
+    } else if (ix->binary) {
+      if (launch_scan_hamming((const uint8_t*)rs.f32, ix->d * 4, begin, end, (const uint8_t*)ws.q_keep, c.nq, state, st)) return 1;
     } else {
       if (launch_scan_fp32(rs.f32, ix->d, ix->metric, begin, end, ws.q_keep, c.nq, state, st)) return 1;
     }
@@ -607,12 +620,18 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
     c.waves += 1;
     begin = end;
   }
-  if (launch_emit(state, c.nq, c.k, ix->metric, ix->id_offset, Ddev, Idev, st)) return 1;
+  if (ix->binary) {
+    if (launch_emit_hamming(state, c.nq, c.k, tensor ? ix->b_nbits : 0, ix->id_offset, (int32_t*)Ddev, Idev, st)) return 1;
+  } else if (launch_emit(state, c.nq, c.k, ix->metric, ix->id_offset, Ddev, Idev, st)) {
+    return 1;
+  }
   c.kernels += 1;
   return 0;
 }
 
-static int find_graph_nodes(SearchGraph& g) {
+static int find_graph_nodes(SearchGraph& g, bool binary) {
+  const void* prep_fn = binary ? prep_binary_kernel_addr() : prep_queries_kernel_addr();
+  const void* emit_fn = binary ? emit_hamming_kernel_addr() : emit_kernel_addr();
   size_t n = 0;
   SSS_CUDA_OK(cudaGraphGetNodes(g.graph, nullptr, &n));
   std::vector<cudaGraphNode_t> nodes(n);
@@ -623,8 +642,8 @@ static int find_graph_nodes(SearchGraph& g) {
     if (t != cudaGraphNodeTypeKernel) continue;
     cudaKernelNodeParams kp;
     SSS_CUDA_OK(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-    if (kp.func == prep_queries_kernel_addr()) g.prep = nodes[i];
-    if (kp.func == emit_kernel_addr()) g.emit = nodes[i];
+    if (kp.func == prep_fn) g.prep = nodes[i];
+    if (kp.func == emit_fn) g.emit = nodes[i];
   }
   SSS_REQUIRE(g.prep != nullptr && g.emit != nullptr, "captured search graph lacks its staging / emit nodes");
   return 0;
@@ -665,7 +684,7 @@ static SearchGraph* capture_graph(sss_index* ix, SearchCtx& c, const float* q_in
     g.destroy();
     return nullptr;
   }
-  if (cudaGraphInstantiate(&g.exec, g.graph, 0) != cudaSuccess || find_graph_nodes(g)) {
+  if (cudaGraphInstantiate(&g.exec, g.graph, 0) != cudaSuccess || find_graph_nodes(g, ix->binary)) {
     cudaGetLastError();
     g.destroy();
     return nullptr;
@@ -695,6 +714,14 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   c.tensor = c.mode != SSS_MODE_FP32 && c.n_rows > 0;
   c.l2_tensor = c.tensor && ix->metric == SSS_METRIC_L2;
   c.rescoring = c.mode != SSS_MODE_FP32;
+  if (ix->binary) {
+    // more than a handful of queries: the +-1 fp8 tensor-core scan; below, the popcount scan over the packed codes
+    // (it reads 32 instead of 256 bytes per row and is bound by the code stream only for nq <= ~4)
+    c.tensor = ix->tensor_ok && c.n_rows > 0 && b.nq > 16;
+    c.rescoring = false;
+    c.l2_tensor = false;
+    c.mode = c.tensor ? SSS_MODE_BF16 : SSS_MODE_FP32;  // (graph key: the two scans are different graphs)
+  }
   ix->stat_variant = 0;
   ix->stat_graph = 0;
   SSS_REQUIRE(b.k <= c.cap / 2, "k too large (max 2048)");
@@ -711,7 +738,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   if (ix->profile && !ix->dbg && dev_alloc(&ix->dbg, 12)) return 1;
   const float* qdev = b.q;
   if (!b.q_on_device) {
-    SSS_CUDA_OK(cudaMemcpyAsync(ws.q_f32, b.q, (size_t)b.nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSS_CUDA_OK(cudaMemcpyAsync(ws.q_f32, b.q, (size_t)b.nq * (size_t)ix->q_row_bytes(), cudaMemcpyHostToDevice, st));
     qdev = ws.q_f32;
   }
   float* Ddev = b.out_on_device ? b.D : ws.out_D;
@@ -732,7 +759,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
             cand.ws_gen == ws.generation)
           g = &cand;
       if (!g) g = capture_graph(ix, c, qdev, Ddev, Idev);
-      if (g && rebind(*g, g->prep, 11, 0, qdev) == 0 && rebind(*g, g->emit, 7, 5, Ddev, 6, Idev) == 0 &&
+      if (g && rebind(*g, g->prep, ix->binary ? 8 : 11, 0, qdev) == 0 && rebind(*g, g->emit, 7, 5, Ddev, 6, Idev) == 0 &&
           cudaGraphLaunch(g->exec, st) == cudaSuccess) {
         g->last_use = ++ix->graph_clock;
         c.kernels = g->kernels;
@@ -800,7 +827,7 @@ static int search_all(sss_index* ix, const float* q, int64_t nq, int k, int mode
   for (int64_t q0 = 0; q0 < nq; q0 += QB) {
     BatchArgs b;
     b.nq = std::min(QB, nq - q0);
-    b.q = q + q0 * ix->d;
+    b.q = (const float*)((const char*)q + q0 * ix->q_row_bytes());
     b.k = k;
     b.mode = mode;
     b.q_on_device = q_on_device != 0;
@@ -896,7 +923,8 @@ extern "C" int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------------
-// binary index
+// binary index: a float index in its binary flavour (packed codes in the fp32 slot of the row store, +-1 E4M3
+// rows in the bf16 slot), driven by the same wave schedule, refine and graph replay
 // ---------------------------------------------------------------------------------------------------
 namespace sss {
 __global__ void repack_codes_kernel(const uint8_t* __restrict__ in, int nbytes, uint8_t* __restrict__ out, int pitch,
@@ -917,15 +945,7 @@ static int launch_repack(const uint8_t* in, int nbytes, uint8_t* out, int pitch,
 }  // namespace sss
 
 struct sss_binary_index {
-  int device = 0, nbits = 0, nbytes = 0, pitch = 0;
-  int64_t id_offset = 0;
-  uint8_t* codes = nullptr;  // [cap_rows, pitch]
-  int64_t n = 0, cap_rows = 0;
-  Workspace ws;
-  uint8_t* q_codes = nullptr;
-  int64_t q_cap = 0;
-  int32_t* out_D = nullptr;
-  int64_t out_elems = 0;
+  sss_index core;
 };
 
 extern "C" int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset) {
@@ -934,140 +954,95 @@ extern "C" int sss_binary_create(sss_binary_index_t** out, int device, int nbits
   int ndev = 0;
   SSS_CUDA_OK(cudaGetDeviceCount(&ndev));
   SSS_REQUIRE(device >= 0 && device < ndev, "sss_binary_create: no such CUDA device");
-  sss_binary_index* ix = new sss_binary_index();
-  ix->device = device;
-  ix->nbits = nbits;
-  ix->nbytes = nbits / 8;
-  ix->pitch = (ix->nbytes + 3) / 4 * 4;
-  ix->id_offset = id_offset;
-  *out = ix;
+  cudaDeviceProp prop;
+  SSS_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  SSS_REQUIRE(prop.major == 10, "libsss_b200 is built for sm_100a only; device is sm_" +
+                                    std::to_string(prop.major * 10 + prop.minor));
+  sss_binary_index* bx = new sss_binary_index();
+  sss_index& ix = bx->core;
+  ix.device = device;
+  ix.binary = true;
+  ix.b_nbits = nbits;
+  ix.b_nbytes = nbits / 8;
+  ix.d = (ix.b_nbytes + 3) / 4;                  // packed pitch in 4-byte words: the fp32 slot holds the codes
+  ix.d_pad = (nbits + 127) / 128 * 128 / 2;      // fp8 row bytes / 2: the geometry of a bf16 row of that many bytes
+  ix.metric = SSS_METRIC_IP;
+  ix.id_offset = id_offset;
+  ix.num_sms = prop.multiProcessorCount;
+  ix.tensor_ok = ix.d_pad <= 128;                // the pair / TS kernels: codes of up to 256 bits (the reference: 250)
+  ix.tune = Tuning::from_env();
+  *out = bx;
   return 0;
 }
 
-extern "C" int sss_binary_destroy(sss_binary_index_t* ix) {
-  if (!ix) return 0;
-  DeviceGuard g(ix->device);
-  dev_free(ix->codes);
-  dev_free(ix->q_codes);
-  dev_free(ix->out_D);
-  ix->ws.release();
-  delete ix;
+extern "C" int sss_binary_destroy(sss_binary_index_t* bx) {
+  if (!bx) return 0;
+  sss_index& ix = bx->core;
+  DeviceGuard g(ix.device);
+  if (g.ok) {
+    cudaDeviceSynchronize();
+    ix.drop_graphs();
+    ix.rows.release();
+    dev_free(ix.dbg);
+    ix.ws.release();
+    for (cudaEvent_t e : ix.ev) cudaEventDestroy(e);
+    if (ix.cap_stream) cudaStreamDestroy(ix.cap_stream);
+  }
+  delete bx;
+  return g.ok ? 0 : 1;
+}
+
+extern "C" int64_t sss_binary_ntotal(const sss_binary_index_t* bx) { return bx ? bx->core.rows.n : 0; }
+extern "C" int64_t sss_binary_stat(const sss_binary_index_t* bx, int what) { return bx ? sss_index_stat(&bx->core, what) : -1; }
+extern "C" int sss_binary_set_profiling(sss_binary_index_t* bx, int on) {
+  SSS_REQUIRE(bx != nullptr, "sss_binary_set_profiling: NULL index");
+  bx->core.profile = on != 0;
   return 0;
 }
 
-extern "C" int64_t sss_binary_ntotal(const sss_binary_index_t* ix) { return ix ? ix->n : 0; }
-
-extern "C" int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream) {
-  SSS_REQUIRE(ix != nullptr, "sss_binary_add: NULL index");
+extern "C" int sss_binary_add(sss_binary_index_t* bx, const uint8_t* codes, int64_t n, int on_device, void* stream) {
+  SSS_REQUIRE(bx != nullptr, "sss_binary_add: NULL index");
   SSS_REQUIRE(n >= 0, "sss_binary_add: negative row count");
   if (n == 0) return 0;
   SSS_REQUIRE(codes != nullptr, "sss_binary_add: NULL codes");
-  DeviceGuard g(ix->device);
+  sss_index& ix = bx->core;
+  SSS_REQUIRE(ix.rows.n + n < 0xFFFFFFF0ll, "sss_binary_add: more than 2^32 rows in one shard");
+  DeviceGuard g(ix.device);
+  SSS_REQUIRE(g.ok, "sss_binary_add: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
-  if (ix->n + n > ix->cap_rows) {
-    int64_t new_cap = std::max<int64_t>(ix->n + n, ix->cap_rows + ix->cap_rows / 2);
-    uint8_t* nc = nullptr;
-    if (dev_alloc(&nc, (size_t)new_cap * ix->pitch)) return 1;
-    if (ix->n > 0) SSS_CUDA_OK(cudaMemcpyAsync(nc, ix->codes, (size_t)ix->n * ix->pitch, cudaMemcpyDeviceToDevice, st));
-    SSS_CUDA_OK(cudaStreamSynchronize(st));
-    dev_free(ix->codes);
-    ix->codes = nc;
-    ix->cap_rows = new_cap;
-  }
+  ix.epoch += 1;
+  ix.drop_graphs();
+  if (ix.rows.ensure(ix.rows.n + n, ix.d, ix.d_pad, ix.tensor_ok, st)) return 1;
   const uint8_t* src = codes;
   uint8_t* staged = nullptr;
   if (!on_device) {
-    if (dev_alloc(&staged, (size_t)n * ix->nbytes)) return 1;
-    SSS_CUDA_OK(cudaMemcpyAsync(staged, codes, (size_t)n * ix->nbytes, cudaMemcpyHostToDevice, st));
+    if (dev_alloc(&staged, (size_t)n * ix.b_nbytes)) return 1;
+    if (cudaMemcpyAsync(staged, codes, (size_t)n * ix.b_nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      cudaFree(staged);
+      set_error("sss_binary_add: host to device copy failed");
+      return 1;
+    }
     src = staged;
   }
-  int rc = launch_repack(src, ix->nbytes, ix->codes + (size_t)ix->n * ix->pitch, ix->pitch, n, st);
+  const int pitch = ix.d * 4;
+  int rc = launch_repack(src, ix.b_nbytes, (uint8_t*)ix.rows.f32 + (size_t)ix.rows.n * pitch, pitch, n, st);
+  if (!rc && ix.tensor_ok)
+    rc = launch_expand_codes_fp8(src, ix.b_nbytes, n, ix.d_pad * 2, (uint8_t*)ix.rows.bf16 + (size_t)ix.rows.n * ix.d_pad * 2, st);
   if (staged) {
     cudaStreamSynchronize(st);
     cudaFree(staged);
   }
   if (rc) return rc;
-  ix->n += n;
+  ix.rows.n += n;
   return 0;
 }
 
-extern "C" int sss_binary_search(sss_binary_index_t* ix, const uint8_t* q, int64_t nq, int k, int q_on_device,
+extern "C" int sss_binary_search(sss_binary_index_t* bx, const uint8_t* q, int64_t nq, int k, int q_on_device,
                                  int32_t* D, int64_t* I, int out_on_device, void* stream) {
-  SSS_REQUIRE(ix != nullptr, "sss_binary_search: NULL index");
-  SSS_REQUIRE(k >= 1 && nq >= 0, "sss_binary_search: bad k / nq");
-  if (nq == 0) return 0;
-  SSS_REQUIRE(q && D && I, "sss_binary_search: NULL buffer");
-  DeviceGuard g(ix->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int cap = 4096;
-  SSS_REQUIRE(k <= cap / 2, "k too large (max 2048)");
-  const int64_t nq_pad = (nq + 127) / 128 * 128;
-  Workspace& ws = ix->ws;
-  if (ws.ensure(nq_pad, cap, 1, 64, out_on_device ? 0 : nq * k)) return 1;
-  if (nq > ix->q_cap) {
-    dev_free(ix->q_codes);
-    ix->q_cap = nq;
-    if (dev_alloc(&ix->q_codes, (size_t)nq * ix->pitch)) return 1;
-  }
-  if (!out_on_device && nq * k > ix->out_elems) {
-    dev_free(ix->out_D);
-    ix->out_elems = nq * k;
-    if (dev_alloc(&ix->out_D, ix->out_elems)) return 1;
-  }
-  const uint8_t* qsrc = q;
-  uint8_t* staged = nullptr;
-  if (!q_on_device) {
-    if (dev_alloc(&staged, (size_t)nq * ix->nbytes)) return 1;
-    SSS_CUDA_OK(cudaMemcpyAsync(staged, q, (size_t)nq * ix->nbytes, cudaMemcpyHostToDevice, st));
-    qsrc = staged;
-  }
-  int rc = launch_repack(qsrc, ix->nbytes, ix->q_codes, ix->pitch, nq, st);
-  int32_t* Ddev = out_on_device ? D : ix->out_D;
-  int64_t* Idev = out_on_device ? I : ws.out_I;
-  for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
-    SelectState state = ws.state();
-    state.cap = cap;
-    rc = launch_prep_queries(nullptr, 0, nq_pad, 1, 64, nullptr, 0, nullptr, state, st);
-    // prep marks every row as padding (nq = 0): reopen the real queries
-    if (!rc) {
-      std::vector<float> neg((size_t)nq, -INFINITY);
-      if (cudaMemcpyAsync(ws.thr, neg.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-          cudaStreamSynchronize(st) != cudaSuccess) {
-        set_error("sss_binary_search: threshold reset failed");
-        rc = 1;
-      }
-    }
-    RefineArgs ra;
-    ra.nq = nq; ra.k = k; ra.reduce_max = 0; ra.row_seg = nullptr; ra.rescore = 0; ra.db_f32 = nullptr;
-    ra.q_f32 = nullptr; ra.d = 0; ra.metric = 0;
-    ra.wave = 0; ra.rec = nullptr; ra.rec_cnt = nullptr; ra.rec_nsub = 0; ra.rec_cap = kRecSubCap; ra.l2_tensor = 0; ra.lazy = 0; ra.final = 1; ra.row_limit = ix->n; ra.debug = nullptr;
-    std::vector<int64_t> ends = make_waves(ix->n, cap, k, attempt == 1, false, 0, Tuning());
-    int64_t begin = 0;
-    for (int64_t end : ends) {
-      if (rc) break;
-      ra.wave += 1;
-      rc = launch_scan_hamming(ix->codes, ix->pitch, begin, end, ix->q_codes, nq, state, st);
-      if (!rc) rc = launch_refine(ra, state, 148, st);
-      begin = end;
-    }
-    if (!rc) rc = launch_emit_hamming(state, nq, k, ix->nbits, ix->id_offset, Ddev, Idev, st);
-    int flag = 0;
-    if (!rc && cudaMemcpyAsync(&flag, ws.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
-    if (!rc && !out_on_device) {
-      if (cudaMemcpyAsync(D, Ddev, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-          cudaMemcpyAsync(I, Idev, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = 1;
-    }
-    if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
-    if (rc || flag == 0) break;
-    if (attempt == 1) {
-      set_error("candidate overflow persisted in the safe wave schedule (internal error)");
-      rc = 1;
-    }
-  }
-  if (staged) cudaFree(staged);
-  if (rc && g_err.empty()) set_error("sss_binary_search: CUDA failure");
-  return rc;
+  SSS_REQUIRE(bx != nullptr, "sss_binary_search: NULL index");
+  // (integer distances travel through the float index's driver: same 4-byte slots, written by the Hamming emit)
+  return search_all(&bx->core, (const float*)q, nq, k, SSS_MODE_EXACT, q_on_device, (float*)D, I, out_on_device, stream,
+                    "sss_binary_search");
 }
 
 extern "C" int sss_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits_in, int on_device, int device,
@@ -1076,6 +1051,7 @@ extern "C" int sss_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int
   SSS_REQUIRE(n >= 0 && nbits_in >= 1, "sss_pack_sign_bits: bad shape");
   if (n == 0) return 0;
   DeviceGuard g(device);
+  SSS_REQUIRE(g.ok, "sss_pack_sign_bits: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (on_device) return launch_pack_sign_bits(x, codes, n, nbits_in, st);
   const int nbytes = (nbits_in + 7) / 8;

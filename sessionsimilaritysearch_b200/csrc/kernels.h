@@ -46,6 +46,8 @@ struct Bf16ScanPlan {
   bool kloop;       // wide rows (d_pad > 128): both operands streamed per K block, one query group per CTA pair
   int groups;       // K-loop variant: query groups of 256
   int last_k4;      // K-loop variant: 16-wide slices of real columns in the last K block
+  bool fp8;         // operands are E4M3 bytes (Hamming search, +-1 codes): set by the caller after planning; rows of
+                    // 2 * d_pad bytes either way, so tiles, tensor maps and the ring are those of the bf16 scan
 };
 // rec_boost multiplies the records per sub-region (1, or 4 after a search that overflowed one)
 // d_used = columns that hold data (d, + 2 for L2); 0 = d_pad
@@ -105,7 +107,16 @@ const void* prep_queries_kernel_addr();
 int launch_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits, cudaStream_t st);
 int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_t row_end, const uint8_t* q, int64_t nq,
                         SelectState st, cudaStream_t stream);
-int launch_emit_hamming(SelectState st, int64_t nq, int k, int nbits, int64_t id_offset, int32_t* D, int64_t* I,
+// dot_bits > 0: scores are +-1 dot products over dot_bits elements (tensor path); 0: scores are -hamming (popcount path)
+int launch_emit_hamming(SelectState st, int64_t nq, int k, int dot_bits, int64_t id_offset, int32_t* D, int64_t* I,
                         cudaStream_t stream);
+// packed codes [n, nbytes] -> +-1.0 E4M3 bytes [n, row_bytes] (row_bytes a multiple of 128, zero padded)
+int launch_expand_codes_fp8(const uint8_t* codes, int nbytes, int64_t n, int row_bytes, uint8_t* out, cudaStream_t st);
+// query staging of a binary search: fp8 rows [nq_pad, row_bytes] (may be NULL), packed rows [nq, pitch] (may be NULL),
+// selection state reset
+int launch_prep_binary(const uint8_t* q_codes, int64_t nq, int64_t nq_pad, int nbytes, int row_bytes, uint8_t* q_fp8,
+                       uint8_t* q_packed, int pitch, SelectState st, cudaStream_t stream);
+const void* prep_binary_kernel_addr();
+const void* emit_hamming_kernel_addr();
 
 }  // namespace sss

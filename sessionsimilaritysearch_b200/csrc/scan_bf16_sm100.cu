@@ -251,7 +251,8 @@ scan_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // TMEM: [0, a_cols) = A (num_mt * num_kb * 32 columns: lane = query, column = two bf16), then two 128-column
 // accumulator slots (slot == epilogue warpgroup).
 // ---------------------------------------------------------------------------------------------------------
-template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
+template <int kCap, bool kFp8>  // records per private sub-region (compile time: the epilogue is sensitive to it);
+                                // kFp8: operands are E4M3 bytes (Hamming search over +-1 codes), same byte geometry
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -337,8 +338,12 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
             const uint32_t a_tmem = tmem_base + (uint32_t)(mt * p.num_kb + kb) * 32u;
             const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)  // K=16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-              umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4) {  // K=16 bf16 (32 fp8) = 8 TMEM columns of A, 32 bytes of the B swizzle row
+              if (kFp8)
+                umma_fp8_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+              else
+                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(tfull_bar + 8 * slot);
         }
@@ -501,6 +506,16 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc2), "r"(accumulate)
       : "memory");
 }
+constexpr uint32_t kIdesc2Fp8 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+__device__ __forceinline__ void umma_fp8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc2Fp8), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
@@ -509,7 +524,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
       : "memory");
 }
 
-template <int kCap>  // records per private sub-region (compile time: the epilogue is sensitive to it)
+template <int kCap, bool kFp8>  // records per private sub-region (compile time: the epilogue is sensitive to it)
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                       const ScanParams p) {
@@ -616,8 +631,12 @@ scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint64_t adesc = umma_desc_sw128(q_smem + (uint32_t)(j * p.num_kb + kb) * kKBlockBytes);
             const uint64_t bdesc = umma_desc_sw128(db_smem + (uint32_t)(stage * p.num_kb + kb) * kKBlockBytes);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (kFp8)
+                umma_fp8_2cta(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+              else
+                umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), (kb | k4) != 0 ? 1u : 0u);
+            }
           }
           umma_commit_2cta(tfull_bar + 8 * slot);
         }
@@ -968,6 +987,7 @@ int plan_scan_bf16(int d_pad, int64_t nq_pad, int num_sms, int max_stages, Bf16S
   SSS_REQUIRE(nq_pad % kTileQ == 0 && nq_pad > 0, "nq_pad must be a positive multiple of 128");
   const int total_mtiles = (int)(nq_pad / kTileQ);
   plan->kloop = false;
+  plan->fp8 = false;
   plan->groups = 0;
   {
     const int tail = (d_used > 0 ? d_used : d_pad) - (d_pad - 64);  // real columns of the last K block
@@ -1079,14 +1099,19 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
   const bool big = plan.rec_cap != kRecSubCap && !plan.kloop;  // boosted sub-regions (after an overflow): 4x
   SSS_REQUIRE(plan.kloop || plan.rec_cap == kRecSubCap || plan.rec_cap == 4 * kRecSubCap, "unsupported record capacity");
   // (per device, per kernel: the attribute lives in the device's context)
-  static SmemAttr a_ss, a_ss4, a_ts, a_ts4, a_pair, a_pair4, a_kloop;
+  static SmemAttr a_ss, a_ss4, a_ts, a_ts4, a_pair, a_pair4, a_kloop, a_ts8, a_ts84, a_pair8, a_pair84;
   const int sb = plan.smem_bytes;
+  SSS_REQUIRE(!plan.fp8 || (!plan.kloop && (plan.two_cta || plan.ts)), "the fp8 (Hamming) scan runs on the pair and TS kernels");
   if (plan.kloop) {
     if (a_kloop.ensure(scan_bf16_kloop_kernel, sb)) return 1;
+  } else if (plan.two_cta && plan.fp8) {
+    if (big ? a_pair84.ensure(scan_bf16_2cta_kernel<4 * kRecSubCap, true>, sb) : a_pair8.ensure(scan_bf16_2cta_kernel<kRecSubCap, true>, sb)) return 1;
   } else if (plan.two_cta) {
-    if (big ? a_pair4.ensure(scan_bf16_2cta_kernel<4 * kRecSubCap>, sb) : a_pair.ensure(scan_bf16_2cta_kernel<kRecSubCap>, sb)) return 1;
+    if (big ? a_pair4.ensure(scan_bf16_2cta_kernel<4 * kRecSubCap, false>, sb) : a_pair.ensure(scan_bf16_2cta_kernel<kRecSubCap, false>, sb)) return 1;
+  } else if (plan.ts && plan.fp8) {
+    if (big ? a_ts84.ensure(scan_bf16_ts_kernel<4 * kRecSubCap, true>, sb) : a_ts8.ensure(scan_bf16_ts_kernel<kRecSubCap, true>, sb)) return 1;
   } else if (plan.ts) {
-    if (big ? a_ts4.ensure(scan_bf16_ts_kernel<4 * kRecSubCap>, sb) : a_ts.ensure(scan_bf16_ts_kernel<kRecSubCap>, sb)) return 1;
+    if (big ? a_ts4.ensure(scan_bf16_ts_kernel<4 * kRecSubCap, false>, sb) : a_ts.ensure(scan_bf16_ts_kernel<kRecSubCap, false>, sb)) return 1;
   } else {
     if (big ? a_ss4.ensure(scan_bf16_kernel<4 * kRecSubCap>, sb) : a_ss.ensure(scan_bf16_kernel<kRecSubCap>, sb)) return 1;
   }
@@ -1108,15 +1133,23 @@ int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* t
     cfg.numAttrs = 1;
     if (plan.kloop)
       SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_kloop_kernel, mq, mdb, p));
+    else if (plan.fp8 && big)
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<4 * kRecSubCap, true>, mq, mdb, p));
+    else if (plan.fp8)
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<kRecSubCap, true>, mq, mdb, p));
     else if (big)
-      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<4 * kRecSubCap>, mq, mdb, p));
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<4 * kRecSubCap, false>, mq, mdb, p));
     else
-      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<kRecSubCap>, mq, mdb, p));
+      SSS_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_bf16_2cta_kernel<kRecSubCap, false>, mq, mdb, p));
   } else if (plan.ts) {
-    if (big)
-      scan_bf16_ts_kernel<4 * kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+    if (plan.fp8 && big)
+      scan_bf16_ts_kernel<4 * kRecSubCap, true><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+    else if (plan.fp8)
+      scan_bf16_ts_kernel<kRecSubCap, true><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+    else if (big)
+      scan_bf16_ts_kernel<4 * kRecSubCap, false><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
     else
-      scan_bf16_ts_kernel<kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
+      scan_bf16_ts_kernel<kRecSubCap, false><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mdb, p);
   } else {
     if (big)
       scan_bf16_kernel<4 * kRecSubCap><<<grid, kNumThreads, plan.smem_bytes, stream>>>(mq, mdb, p);

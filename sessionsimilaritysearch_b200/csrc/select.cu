@@ -652,16 +652,37 @@ __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restr
   const int need = (k - 1) * chunk_gap + 1;
   if (need > n_chunks) return;
   {
+    // 16 independent loads in flight per thread: with a handful of blocks (few queries) this phase is pure latency
     const int qq = tid & 7;
-    for (int i = tid >> 3; i < n_chunks; i += 32)
-      bs_keys[qq * pitch + i] = score_key(cmax[(size_t)i * (size_t)nq_pad + (size_t)(q0 + qq)]);
+    for (int i0 = tid >> 3; i0 < n_chunks; i0 += 32 * 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + 32 * u;
+        v[u] = i < n_chunks ? cmax[(size_t)i * (size_t)nq_pad + (size_t)(q0 + qq)] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < n_chunks) bs_keys[qq * pitch + i] = score_key(v[u]);
+      }
+    }
   }
   __syncthreads();
   const int64_t q = q0 + warp;
   if (q >= nq) return;
   const uint32_t* keys = bs_keys + warp * pitch;
-  uint32_t prefix = 0u;  // largest value v with count(keys >= v) >= need, built bit by bit = the need-th largest key
-  for (int bit = 31; bit >= 0; --bit) {
+  // bits above the highest one in which the keys differ are common to all of them
+  uint32_t diff = 0u;
+  const uint32_t k0 = keys[0];
+  for (int i = lane; i < n_chunks; i += 32) diff |= keys[i] ^ k0;
+  diff = __reduce_or_sync(0xffffffffu, diff);
+  const int top = diff ? 31 - __clz(diff) : -1;
+  // largest v (low 8 bits left zero: any lower bound of the need-th largest key is a valid threshold, and 2^-15
+  // relative is far inside the slack) with count(keys >= v) >= need, built bit by bit
+  uint32_t prefix = top >= 31 ? 0u : (k0 & ~((2u << top) - 1u));
+  if (top < 0) prefix = k0;
+  for (int bit = top; bit >= 8; --bit) {
     const uint32_t cand = prefix | (1u << bit);
     int cnt = 0;
     for (int i = lane; i < n_chunks; i += 32) cnt += keys[i] >= cand ? 1 : 0;

@@ -79,6 +79,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileRows >> 3) << 17) |
                             ((uint32_t)(kTileQ >> 4) << 24);
 
+// kind::f8f6f4 instruction descriptor, E4M3 x E4M3 -> fp32 (format code 0), M=128, N=128: K = 32 elements = the same
+// 32 bytes of a swizzle row as K = 16 bf16, so the fp8 scans share every address computation with the bf16 ones.
+// Used for Hamming search: codes stored as +-1.0 in E4M3 (0x38 / 0xB8), <a, b> = nbits - 2 * hamming, exact in fp32.
+constexpr uint32_t kIdescFp8 = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\t"
@@ -97,6 +102,15 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_fp8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(kIdescFp8), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {

@@ -170,6 +170,16 @@ class IndexBinaryFlat:
     def ntotal(self):
         return int(self._lib.sss_binary_ntotal(self._h))
 
+    def set_profiling(self, on=True):
+        check(self._lib.sss_binary_set_profiling(self._h, int(bool(on))))
+
+    def stats(self):
+        st = self._lib.sss_binary_stat
+        return {"kernels": int(st(self._h, 0)), "waves": int(st(self._h, 1)), "reruns": int(st(self._h, 2)),
+                "scan_ns": int(st(self._h, 3)), "scan_launches": int(st(self._h, 4)),
+                "overflow_reason": int(st(self._h, 24)), "graph": int(st(self._h, 26)),
+                "scan_variant": ("popcount", "ss", "ts", "2cta", "kloop")[int(st(self._h, 25))]}
+
     def _codes(self, x):
         if _is_torch(x):
             import torch

@@ -450,3 +450,50 @@ def test_graph_replay_follows_new_buffers_and_index_changes(sss, oracle):
     D, I = ix.search(q, 20)
     Do, Io = oracle.search_flat(dbn, q[::32], 20)
     _assert_exact(D[::32], I[::32], Do, Io)
+
+
+@pytest.mark.parametrize("nbits,n,nq,k", [(256, 400000, 200, 100), (256, 400000, 8, 100), (128, 300000, 130, 50),
+                                           (64, 300000, 600, 100), (512, 50000, 40, 20), (256, 3000, 33, 100)])
+def test_binary_hamming_tensor_and_popcount_paths(sss, oracle, nbits, n, nq, k):
+    """faiss.IndexBinaryFlat semantics (fine_tune_ours.py:839-843,871-876) at sizes that take the bootstrapped schedule:
+    more than 16 queries over codes of <= 256 bits run as a +-1 E4M3 tensor-core scan, fewer queries (or 512-bit codes)
+    as a popcount scan; both must equal the oracle bit for bit — distances and ids, ties (the norm for integer
+    distances: 64-bit codes over 300K rows tie by the thousand) going to the smaller id."""
+    rng = np.random.default_rng(nbits + n + nq)
+    codes = rng.integers(0, 256, size=(n, nbits // 8), dtype=np.uint8)
+    centres = codes[rng.integers(0, n, size=nq)].copy()
+    flip = rng.random((nq, nbits // 8, 8)) < 0.08
+    qcodes = centres ^ np.packbits(flip, axis=2).reshape(nq, nbits // 8)
+    ix = sss.IndexBinaryFlat(nbits)
+    ix.add(codes[:n // 3])
+    ix.add(codes[n // 3:])              # ragged adds
+    D, I = ix.search(qcodes, k)
+    st = ix.stats()
+    tensor = nq > 16 and nbits <= 256
+    assert (st["scan_variant"] in ("ts", "2cta")) == tensor, st
+    assert st["reruns"] == 0, st
+    Do, Io = oracle.search_hamming(codes, qcodes, k)
+    assert D.dtype == np.int32 and np.array_equal(D, Do) and np.array_equal(I, Io)
+    import torch
+    Dt, It = ix.search(torch.from_numpy(qcodes).cuda(), k)      # device in / out, graph replay
+    assert ix.stats()["graph"] == 1
+    assert np.array_equal(Dt.cpu().numpy(), Do) and np.array_equal(It.cpu().numpy(), Io)
+
+
+def test_binary_reference_shape_250_bits(sss, oracle):
+    """the reference's own shape: BinarizeHead(1600, 250) outputs in {-1, 0, +1} -> (d + 1) / 2 -> astype(int) ->
+    np.packbits (250 -> 256 bits, zero padded) -> IndexBinaryFlat(256)"""
+    rng = np.random.default_rng(77)
+    x = np.sign(rng.standard_normal((300000, 250))).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = 0
+    codes = sss.pack_sign_bits(x)
+    assert np.array_equal(codes, np.packbits(((x + 1) / 2).astype(int), axis=1))
+    qx = x[rng.integers(0, x.shape[0], size=100)].copy()
+    qx[rng.random(qx.shape) < 0.1] *= -1
+    qcodes = sss.pack_sign_bits(qx)
+    ix = sss.IndexBinaryFlat(codes.shape[1] * 8)
+    ix.add(codes)
+    D, I = ix.search(qcodes, 100)
+    Do, Io = oracle.search_hamming(codes, qcodes, 100)
+    assert np.array_equal(D, Do) and np.array_equal(I, Io)
+    assert ix.stats()["scan_variant"] == "ts"
