@@ -138,10 +138,10 @@ int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k,
 /* ---- binary index (replaces faiss.IndexBinaryFlat, fine_tune_ours.py:839-843,871-876) ------------ */
 
 /* nbits must be a multiple of 8, <= 512; codes are uint8 [n, nbits/8] as produced by np.packbits(axis=1).
- * Searches of more than 16 queries over codes of up to 256 bits (the reference hashes to 250) run on the tensor
- * cores: the index also keeps every code as +-1.0 in E4M3 (one byte per bit), <a, b> = nbits - 2 * hamming is exact
- * in the fp32 accumulators, and the fused scan + streaming top-k of the float index applies unchanged (bootstrap
- * thresholds, waves, graph replay).  Fewer queries, or longer codes, take a popcount scan over the packed codes. */
+ * Codes of up to 256 bits (the reference hashes to 250) are searched on the tensor cores: the index also keeps
+ * every code as +-1.0 in E4M3 (one byte per bit), <a, b> = nbits - 2 * hamming is exact in the fp32 accumulators,
+ * and the fused scan + streaming top-k of the float index applies unchanged (bootstrap thresholds, waves, graph
+ * replay).  Longer codes take a popcount scan over the packed codes. */
 int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset);
 int sss_binary_destroy(sss_binary_index_t* ix);
 int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream);
@@ -176,7 +176,8 @@ int sss_item_vote(const float* D, const int64_t* I, int64_t nq, int s, const int
 /* ---- session encoder (replaces UnifyPoolingGraphLevelEncoder.forward after the text embedder) ----- */
 
 /* Shapes of the reference model (pretrain_filtered_amazon.py:262-287): in_dim 768, hidden 800,
- * layers 3, out 1600, max_seq_len 20.  Weights are fp32, row-major [out, in] as in torch state_dicts. */
+ * layers 3, out 1600, max_seq_len 20.  Weights are fp32, row-major [out, in] as in torch state_dicts.
+ * in_dim and hidden must be multiples of 8 (the layers read 16-byte aligned slices of one bf16 operand buffer). */
 typedef struct sss_encoder_shape {
   int in_dim;      /* 768 */
   int hidden;      /* 800 */
@@ -232,16 +233,16 @@ typedef struct sss_encoder_io {
 } sss_encoder_io_t;
 int sss_encoder_forward_ex(sss_encoder_t* enc, const sss_graph_batch_t* batch, const sss_encoder_io_t* io, void* stream);
 
-/* Arithmetic of the encoder's dense linears.  SSS_ENCODER_MATH_FP32 (default): cuBLAS sgemm, pedantic fp32 on the
- * CUDA cores.  SSS_ENCODER_MATH_BF16X9: cuBLAS' fp32 emulation on the bf16 tensor cores (each operand split into
- * three bf16 terms, nine products, fp32-level accuracy; cuBLAS >= 12.9 on sm_100) — returns non-zero and leaves the
- * mode unchanged when the loaded cuBLAS does not offer it.  SSS_ENCODER_MATH_BF16X3: this library's own tcgen05 GEMM
- * (csrc/gemm_bf16x3_sm100.cu): operands split into hi + lo bf16, three products accumulated in fp32 in TMEM; through
- * the whole encoder 2.7e-5 of the output scale from a float64 forward (pedantic fp32: 2.5e-6).
- * sss_encoder_get_math returns the active mode. */
+/* Arithmetic of the encoder's dense linears: this library's own tcgen05 GEMM (csrc/gemm_bf16x3_sm100.cu) — operands
+ * split into hi + lo bf16, three products accumulated in fp32 in TMEM; through the whole encoder 2.7e-5 of the output
+ * scale from a float64 forward — with the work that follows each linear (attention logits, GRU gates, tanh / positional
+ * concat, gated attention) fused into its epilogue.  It is the only arithmetic: sss_encoder_set_math accepts
+ * SSS_ENCODER_MATH_BF16X3 and rejects the cuBLAS modes of earlier versions (there is no library GEMM behind this ABI
+ * any more).  sss_encoder_stat(enc, 0) = kernels launched by the last forward. */
 enum { SSS_ENCODER_MATH_FP32 = 0, SSS_ENCODER_MATH_BF16X9 = 1, SSS_ENCODER_MATH_BF16X3 = 2 };
 int sss_encoder_set_math(sss_encoder_t* enc, int math);
 int sss_encoder_get_math(const sss_encoder_t* enc);
+int64_t sss_encoder_stat(const sss_encoder_t* enc, int what);
 
 /* Row gather on the device: out[i, :] = table[ids[i], :] (fp32 [n_rows, d], int64 ids [n], out [n, d]).  Replaces the
  * nn.Embedding lookup of NodeAsinEmbedding.forward (model/NodeEmbedding.py:137-138) and serves the text-feature cache

@@ -16,12 +16,10 @@ from sessionsimilaritysearch_b200 import graph, sessions  # noqa: E402
 
 def main():
     n_batches = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-    math = sys.argv[2] if len(sys.argv) > 2 else "fp32"
     batch = 200
     in_dim, hidden, n_layers, out_dim, msl = 768, 800, 3, 1600, 20
     P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 11)
     enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl, device=0)
-    enc.set_math(math)
     _, graphs = ec.make_graphs(batch * n_batches, in_dim, 17, sessions.sequence_to_graph)
     batches = [graph.collate(graphs[i:i + batch]).to("cuda:0") for i in range(0, len(graphs), batch)]
     for b in batches[:2]:
@@ -35,8 +33,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        print("batch: %d query + %d product nodes, device %.3f ms, wall %.3f ms" % (
-            b['query'].x.shape[0], b['product'].x.shape[0], e0.elapsed_time(e1), (t1 - t0) * 1e3))
+        print("batch: %d query + %d product nodes, device %.3f ms, wall %.3f ms, %d launches" % (
+            b['query'].x.shape[0], b['product'].x.shape[0], e0.elapsed_time(e1), (t1 - t0) * 1e3, enc.launches))
 
 
 if __name__ == "__main__":

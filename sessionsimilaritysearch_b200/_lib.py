@@ -96,6 +96,7 @@ SIGNATURES = {
     "sss_featurize_batch": (c_int, [ctypes.POINTER(FlatSessions), c_i64, ctypes.POINTER(GraphArrays), c_int]),
     "sss_encoder_set_math": (c_int, [c_vp, c_int]),
     "sss_encoder_get_math": (c_int, [c_vp]),
+    "sss_encoder_stat": (c_i64, [c_vp, c_int]),
     "sss_binarize_head": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_vp]),
 }
 

@@ -4,7 +4,7 @@ bench.py --configs ...,binary; returns one dict."""
 import numpy as np
 
 
-def run(env, a, rows=None, nq_list=(1000, 128, 8), k=100):
+def run(env, a, rows=None, nq_list=(1000, 128, 1), k=100):
     import sessionsimilaritysearch_b200 as sss
     torch = env.torch
     rows = int(rows or a.rows_100m)

@@ -715,9 +715,10 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   c.l2_tensor = c.tensor && ix->metric == SSS_METRIC_L2;
   c.rescoring = c.mode != SSS_MODE_FP32;
   if (ix->binary) {
-    // more than a handful of queries: the +-1 fp8 tensor-core scan; below, the popcount scan over the packed codes
-    // (it reads 32 instead of 256 bytes per row and is bound by the code stream only for nq <= ~4)
-    c.tensor = ix->tensor_ok && c.n_rows > 0 && b.nq > 16;
+    // codes of up to 256 bits: the +-1 fp8 tensor-core scan for every batch size (at 100M x 256 bit: 63 K queries/s
+    // = 3.2 PFLOP/s fp8 at nq = 1000, and a 6.3 TB/s code stream at nq <= 128: profiles/r02_binary.md); longer codes
+    // take the popcount scan over the packed codes
+    c.tensor = ix->tensor_ok && c.n_rows > 0;
     c.rescoring = false;
     c.l2_tensor = false;
     c.mode = c.tensor ? SSS_MODE_BF16 : SSS_MODE_FP32;  // (graph key: the two scans are different graphs)

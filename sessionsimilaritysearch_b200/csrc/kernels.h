@@ -1,5 +1,6 @@
 // kernels.h — host-side launchers of every kernel in libsss_b200 (all return 0 / non-zero + set_error).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -59,11 +60,53 @@ int make_tensor_map_bf16_2d(void* out_map128, const void* base, uint64_t rows, u
 int launch_scan_bf16(const Bf16ScanPlan& plan, const void* tmap_q, const void* tmap_db, const void* q_bf16,
                      int64_t row_begin, int64_t row_end, SelectState st, HitRecord* rec, uint32_t* rec_cnt,
                      int* err_flag, float* cmax, cudaStream_t stream);
-// gemm_bf16x3_sm100.cu — split-bf16 tensor-core GEMM of the encoder: C[M,N] = A[M,K] * B[N,K]^T
+// gemm_bf16x3_sm100.cu — split-bf16 tensor-core GEMM of the encoder with fused epilogues: C[M,N] = A[M,K] * B[N,K]^T
+// row_map (optional, device): output row r of the split takes source row row_map[r] (< 0: a zero row)
 int launch_split_bf16(const float* x, int rows, int cols, int64_t ld, int transposed, void* hi, void* lo, int rows_pad,
-                      int cols_pad, cudaStream_t stream);
-int launch_gemm_bf16x3(const void* a_hi, const void* a_lo, int m_pad, const void* b_hi, const void* b_lo, int n_pad,
-                       int k_pad, float* C, int M, int N, int ldc, int* err_flag, cudaStream_t stream);
+                      int cols_pad, cudaStream_t stream, const int* row_map = nullptr);
+enum { EPI_STORE = 0, EPI_ATT = 1, EPI_GRU = 2, EPI_POOL = 3, EPI_ATTPOOL = 4 };
+struct GemmProblem {
+  // operands: hi / lo bf16, K-major, row pitch in elements (a multiple of 64); A is read from column a_k0 on
+  const void *a_hi, *a_lo;
+  int a_rows_pad, a_ld, a_k0;
+  const void *b_hi, *b_lo;
+  int b_rows_pad, b_ld;
+  int M, N;          // real output rows / columns (N only bounds the stores)
+  int bn, tiles_n;   // N tile (128, or 96 for EPI_GRU) and their number
+  int num_kb, last_k4;  // 64-wide K blocks; 16-wide slices of real columns in the last one (1..4)
+  int epi;
+  float* C;          // EPI_STORE / EPI_ATT: fp32 output; EPI_GRU: next features (fp32)
+  int ldc;
+  const float* bias;  // EPI_STORE (optional), EPI_POOL, EPI_ATTPOOL
+  int sign_out;       // EPI_STORE: numerically sign(v) (BinarizeHead)
+  // EPI_ATT: N is a sequence of parts of att_tiles_per_part tiles; part p < 4 with att[p] != NULL gets, per row and
+  // tile, the partial <C[row, tile's columns], att[p]> in att_out[p][row * att_tiles_per_part + tile]
+  const float* att[4];
+  float* att_out[4];
+  int att_tiles_per_part, att_width;
+  // EPI_GRU
+  const float* gru_gh; int gru_gh_ld;
+  const float *gru_b_ih, *gru_b_hh;
+  const float* gru_x; int gru_x_ld, gru_in_w;
+  const float* gru_gp;
+  int gru_H;
+  // hi / lo bf16 copies of what the epilogue produces (EPI_GRU: columns out_k0 + unit; EPI_POOL: columns as in U)
+  __nv_bfloat16 *out_hi, *out_lo;
+  int out_ld, out_k0;
+  // EPI_POOL
+  int pool_is_product, pool_row0, pool_lin_w, pool_msl;
+  const int* pool_prefix;     // products: occurrence rows [prefix[p], prefix[p + 1])
+  const int64_t* pool_pos;    // pos_emb_id per occurrence (products) / per node (queries)
+  const float* pool_pe;       // [msl, msl]
+  float* pool_U;              // [n_expanded + n_query, lin_w + msl]
+  // EPI_ATTPOOL
+  const float* ap_bc;         // [n_graphs, N]
+  const int* ap_node_graph;
+  const float* ap_w;
+  float* ap_out;              // [M, tiles_n] partial attention logits
+};
+// one launch = one or two independent problems (their tiles are enumerated back to back)
+int launch_gemm_bf16x3(const GemmProblem* problems, int n_problems, int* err_flag, cudaStream_t stream);
 // select.cu — bootstrap thresholds from chunk maxima: thr[q] = just below (2k-th largest chunk max - slack)
 int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq_pad, int k, int chunk_gap,
                          float slack_mult, SelectState st, cudaStream_t stream);

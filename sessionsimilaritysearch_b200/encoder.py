@@ -38,8 +38,8 @@ class SessionEncoder:
         check(self._lib.sss_encoder_create(ctypes.byref(h), self.device, ctypes.byref(shape)))
         self._h = h
         self.load_state_dict(params)
-        # dense linears: this library's split-bf16 tcgen05 GEMM by default (2.7e-5 of the output scale from float64);
-        # math="fp32" selects cuBLAS' pedantic sgemm (2.5e-6), the C ABI's own default
+        # dense linears: this library's split-bf16 tcgen05 GEMM (2.7e-5 of the output scale from float64), the only
+        # arithmetic of the C ABI
         self.set_math(math)
 
     @classmethod
@@ -64,15 +64,19 @@ class SessionEncoder:
         return n
 
     def set_math(self, math):
-        """'fp32' (cuBLAS pedantic sgemm, default), 'bf16x3' (this library's tcgen05 GEMM on split-bf16 operands:
-        fp32-level accuracy on the tensor cores) or 'bf16x9' (cuBLAS' fp32 emulation; raises RuntimeError when the
-        loaded cuBLAS does not offer it)"""
+        """'bf16x3': this library's tcgen05 GEMM on split-bf16 operands (fp32-level accuracy on the tensor cores);
+        the cuBLAS arithmetics of earlier versions ('fp32', 'bf16x9') raise RuntimeError"""
         check(self._lib.sss_encoder_set_math(self._h, {"fp32": 0, "bf16x9": 1, "bf16x3": 2}[math]))
         return self
 
     @property
     def math(self):
         return ("fp32", "bf16x9", "bf16x3")[int(self._lib.sss_encoder_get_math(self._h))]
+
+    @property
+    def launches(self):
+        """kernels launched by the last forward"""
+        return int(self._lib.sss_encoder_stat(self._h, 0))
 
     def eval(self):
         return self

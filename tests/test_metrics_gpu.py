@@ -121,8 +121,7 @@ def test_standalone_gnn_pooling_and_get_node_agree_with_the_forward():
     in_dim, hidden, n_layers, out_dim, msl = 24, 32, 3, 60, 20
     _, graphs = ec.make_graphs(12, in_dim, 7, sessions.sequence_to_graph)
     P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 7)
-    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl,
-                             math="fp32")
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
     data = graph.collate(graphs).to("cuda")
     out = enc(data)
     out2, nodes = enc(data, get_node=True)
