@@ -331,7 +331,7 @@ __global__ void graph_mean_hilo_kernel(const float* __restrict__ U, int W, const
   const int g = blockIdx.x;
   const int p0 = ranges[g * 4], p1 = ranges[g * 4 + 1], q0 = ranges[g * 4 + 2], q1 = ranges[g * 4 + 3];
   const float cnt = fmaxf((float)((p1 - p0) + (q1 - q0)), 1.0f);
-  for (int c = threadIdx.x * 4; c < W; c += blockDim.x * 4) {
+  for (int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4; c < W; c += gridDim.y * blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const bool vec = c + 4 <= W;
     for (int pass = 0; pass < 2; ++pass) {
@@ -366,7 +366,7 @@ __global__ void graph_weighted_mean_kernel(const float* __restrict__ U, int W, c
       s_att[i] = sum_parts(att_part + (size_t)r * parts, parts);
     }
     __syncthreads();
-    for (int c = threadIdx.x * 4; c < W; c += blockDim.x * 4) {
+    for (int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4; c < W; c += gridDim.y * blockDim.x * 4) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const bool vec = c + 4 <= W;
       if (base > 0)
@@ -387,7 +387,7 @@ __global__ void graph_weighted_mean_kernel(const float* __restrict__ U, int W, c
       for (int t = 0; t < 4 && c + t < W; ++t) out[(size_t)g * W + c + t] = last ? acc[t] / cnt : acc[t];
     }
   }
-  if (nr == 0)
+  if (nr == 0 && blockIdx.y == 0)
     for (int c = threadIdx.x; c < W; c += blockDim.x) out[(size_t)g * W + c] = 0.0f;
 }
 
@@ -600,7 +600,7 @@ GemmProblem make_problem(const void* a_hi, const void* a_lo, int M, int a_ld, in
   g.M = M;
   g.N = N;
   g.bn = bn;
-  g.tiles_n = (bn == 96) ? (N + 95) / 96 : (N + 127) / 128;
+  g.tiles_n = (N + bn - 1) / bn;
   g.num_kb = (K + 63) / 64;
   const int tail = K - (g.num_kb - 1) * 64;
   g.last_k4 = (tail + 15) / 16;
@@ -735,7 +735,7 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
   const int NQp = pad_to(NQ, 128), NPp = pad_to(NP, 128);
   const int NT = NE + NQ, NTp = pad_to(NT, 128), Bp = pad_to(B, 128);
   const int LDQ = 2 * PP, LDP = 3 * PP + GH;
-  const int tiles_out = pad_to(OUT, 128) / 128;
+  const int tiles_out = (OUT + 127) / 128;   // N tiles across the pooling width: partial attention logits per row
   float *Zq = io->z_query, *Zp = io->z_product;  // node embeddings [N, in + layers * hidden]: the caller's or ours
   float *Sq, *Sp, *asq, *adq, *adp, *asp, *Gp, *U, *Bc, *att_part;
   __nv_bfloat16 *zq_hi, *zq_lo, *zp_hi, *zp_lo, *agg_hi, *agg_lo, *u_hi, *u_lo, *c_hi, *c_lo;
@@ -889,7 +889,8 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
     gp2[s].out_ld = OUTp;
   }
   if (launch_gemm_bf16x3(gp2, 2, e->gemm_flag, st)) return 1;
-  graph_mean_hilo_kernel<<<B, 256, 0, st>>>(U, OUT, ranges, c_hi, c_lo, OUTp);
+  const int col_blocks = std::max(1, std::min(8, (OUT + 1023) / 1024));  // 1024 columns per block: one pass
+  graph_mean_hilo_kernel<<<dim3(B, col_blocks), 256, 0, st>>>(U, OUT, ranges, c_hi, c_lo, OUTp);
   GemmProblem gc = make_problem(c_hi, c_lo, B, OUTp, 0, OUT, e->w_coarse, OUT, 128, EPI_STORE);
   gc.C = Bc;
   gc.ldc = OUT;
@@ -901,7 +902,7 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
   gn.ap_w = wa;
   gn.ap_out = att_part;
   if (launch_gemm_bf16x3(&gn, 1, e->gemm_flag, st)) return 1;
-  graph_weighted_mean_kernel<<<B, 256, 1024 * sizeof(float), st>>>(U, OUT, ranges, att_part, tiles_out, out);
+  graph_weighted_mean_kernel<<<dim3(B, col_blocks), 256, 1024 * sizeof(float), st>>>(U, OUT, ranges, att_part, tiles_out, out);
   e->launches += 5;
   SSS_CUDA_OK(cudaGetLastError());
   return ws_end(e, st);

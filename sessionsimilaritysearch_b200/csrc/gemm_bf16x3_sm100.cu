@@ -8,23 +8,32 @@
 // the output scale from a float64 forward, ten times inside the parity tolerance.  Replaces the x @ W.T of
 // torch.nn.Linear / GATConv.lin_src / GRUCell inside model/gnn.py:64-81,193-217.
 //
-// One CTA per 128 x BN output tile (BN = 128, or 96 for the GRU GEMM), 256 threads, warp-specialised:
-//   warp 0  TMA producer: per 64-wide K block one stage [Ah | Al | Bh | Bl] of SWIZZLE_128B boxes; A is read at a
-//           column offset (the layer's slice of the concatenated node embeddings), the last K block may hold
-//           fewer than four 16-wide slices of real columns
-//   warp 1  MMA issuer: 3 products x 4 (K = 16) tcgen05.mma kind::f16 per stage into one accumulator
+// Persistent CTAs (one per SM, 256 threads, warp-specialised) walk the 128 x BN output tiles (BN = 128, or 96 for the
+// GRU GEMM) of up to two independent problems — the query-side and the product-side linears of a layer, or the two
+// pooling projections, run as ONE launch:
+//   warp 0  TMA producer: per 64-wide K block one stage [Ah | Al | Bh | Bl] of SWIZZLE_128B boxes through a 3-stage
+//           ring; A is read at a column offset (the layer's slice of the concatenated node embeddings), the last K
+//           block may hold fewer than four 16-wide slices of real columns
+//   warp 1  MMA issuer: 3 products x 4 (K = 16) tcgen05.mma kind::f16 per stage into one of TWO TMEM accumulators, so
+//           the next tile's main loop runs while the previous tile is still in its epilogue
 //   warp 2  TMEM allocator
-//   warps 4-7  epilogue: a thread owns one output row; 32 accumulator columns at a time
-// A launch carries up to two independent problems (blockIdx.x enumerates the tiles of both): the query-side and the
-// product-side linears of a layer, or the two pooling projections, run as ONE launch.
+//   warps 4-7  epilogue, 32 accumulator columns at a time: tcgen05.ld (a thread owns one output row; row-wise
+//           reductions finish here), then a [128][33] shared-memory transpose so that consecutive threads touch
+//           consecutive columns of global memory (a thread-per-row epilogue wrote 32 different sectors per
+//           instruction: the GRU epilogue alone took 90 us per launch that way)
+// What bounds it at the encoder's sizes (profiles/r02_encoder.md): not the tensor pipe (25-35 % active) and not L2
+// bandwidth (10 %) but the latency of the operand stream — 192 KB of ring per SM against ~2 us of TMA round trip is
+// ~1300 cycles per 64 KB stage against 768 cycles of MMA — and one or two tiles per SM per launch.  A cta_group::2
+// form with 256 x 256 pair tiles (half the operand bytes per flop) was built and measured SLOWER (0.78 vs 0.69 ms per
+// forward: twice the serial epilogue per CTA, a cross-CTA hop per stage) and is not kept.
 //
 // Epilogues (what the reference does right after the linear, fused so that no activation makes an extra trip
 // through HBM and no separate split / rowdot / GRU / tanh kernel is launched):
 //   EPI_STORE    C (+ bias) as fp32; optionally sign() (BinarizeHead, model/model.py:137)
 //   EPI_ATT      C as fp32 + per-row partial dot products with the GAT attention vectors (GATConv's a_s / a_d,
 //                SURVEY appendix A), one partial per (row, N tile) summed in a fixed order by the consumer
-//   EPI_GRU      GRUCell gates + HeteroConv sum + relu (model/gnn.py:59,72): the weight rows are permuted so that an
-//                N tile of 96 columns holds the r, z, n gates of the same 32 hidden units; writes the next layer's
+//   EPI_GRU      GRUCell gates + HeteroConv sum + relu (model/gnn.py:59,72): the weight rows are permuted so that
+//                an N tile of 96 columns holds the r, z, n gates of the same 32 hidden units; writes the next layer's
 //                product features as fp32 AND as the hi / lo bf16 operand of the next GEMM
 //   EPI_POOL     tanh([lin + b | PE[pos]]) of PositionalAttentionPooling (model/gnn.py:199-206) including the
 //                repeat_interleave of product rows by their occurrence count; writes U as fp32 and hi / lo
@@ -43,18 +52,21 @@ namespace {
 constexpr int kGemmThreads = 256;
 constexpr int kGemmStageBytes = 4 * kKBlockBytes;  // Ah | Al | Bh | Bl
 constexpr int kGemmStages = 3;
-constexpr uint32_t kGemmTmemCols = 128;
-constexpr int kGemmSmemBytes = 1024 + kGemmStages * kGemmStageBytes + 256;
+constexpr uint32_t kGemmTmemCols = 256;            // two accumulators of 128 columns
+constexpr int kGemmXposePitch = 33;
+constexpr int kGemmXposeBytes = 128 * kGemmXposePitch * 4;
+constexpr int kGemmSmemBytes = 1024 + kGemmStages * kGemmStageBytes + kGemmXposeBytes + 256;
 
 struct GemmLaunch {
   GemmProblem p[2];
   int n_problems;
-  int tiles0;  // tiles of problem 0 (blockIdx.x below this belongs to it)
+  int tiles0;       // tiles of problem 0 (global tile index below this belongs to it)
+  int tiles_total;
   int* err_flag;
 };
 
 __device__ __forceinline__ void umma_bf16_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
-                                            uint32_t idesc) {
+                                                 uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
@@ -69,56 +81,29 @@ __device__ __forceinline__ void store_hilo(__nv_bfloat16* hi, __nv_bfloat16* lo,
   hi[idx] = h;
   lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
-
-// ---- epilogues: thread = one output row, r[32] = accumulator columns [col0, col0 + 32) of the tile --------------
-__device__ __forceinline__ void epi_store(const GemmProblem& g, int row, int n0, int c, const uint32_t (&r)[32]) {
-  float* crow = g.C + (size_t)row * (size_t)g.ldc;
-  const int col0 = n0 + c * 32;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int col = col0 + i;
-    if (col < g.N) {
-      float v = __uint_as_float(r[i]);
-      if (g.bias) v += g.bias[col];
-      if (g.sign_out) {
-        const float s = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);
-        const float th = tanhf(v);
-        v = (s - th) + th;  // (sign - tanh).detach() + tanh, model/model.py:137
-      }
-      crow[col] = v;
-    }
-  }
+// sigmoid / tanh on the special-function unit (ex2.approx + rcp.approx, ~1e-6 absolute): the epilogue warps are the
+// only ones doing arithmetic on their scheduler, and the libm forms (25 instructions for tanhf) made the epilogue of
+// the GRU and pooling GEMMs longer than their main loops
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * xc));
 }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
-__device__ __forceinline__ void epi_pool(const GemmProblem& g, int row, int n0, int c, const uint32_t (&r)[32]) {
-  // output rows of this input row: a query -> one row after the product occurrences; a product -> one per occurrence
-  int t0, t1;
-  if (g.pool_is_product) {
-    t0 = g.pool_prefix[row];
-    t1 = g.pool_prefix[row + 1];
-  } else {
-    t0 = g.pool_row0 + row;
-    t1 = t0 + 1;
-  }
-  const int col0 = n0 + c * 32;
-  const int W = g.pool_lin_w + g.pool_msl;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int col = col0 + i;
-    v[i] = col < g.pool_lin_w ? tanhf(__uint_as_float(r[i]) + g.bias[col]) : 0.0f;
-  }
-  for (int t = t0; t < t1; ++t) {
-    const int64_t pos = g.pool_pos[g.pool_is_product ? t : row];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int col = col0 + i;
-      if (col >= W) continue;
-      const float x = col < g.pool_lin_w ? v[i] : tanhf(g.pool_pe[pos * g.pool_msl + (col - g.pool_lin_w)]);
-      g.pool_U[(size_t)t * W + col] = x;
-      store_hilo(g.out_hi, g.out_lo, (size_t)t * g.out_ld + col, x);
-    }
-  }
+struct TileRef {
+  int which, tile_m, tile_n, m0, n0;
+};
+__device__ __forceinline__ TileRef tile_of(const GemmLaunch& L, int t) {
+  TileRef r;
+  r.which = t >= L.tiles0 ? 1 : 0;
+  const GemmProblem& g = L.p[r.which];
+  const int local = t - (r.which ? L.tiles0 : 0);
+  r.tile_n = local % g.tiles_n;
+  r.tile_m = local / g.tiles_n;
+  r.m0 = r.tile_m * kTileQ;
+  r.n0 = r.tile_n * g.bn;
+  return r;
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -131,38 +116,41 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int which = (int)blockIdx.x >= L.tiles0 ? 1 : 0;
-  const GemmProblem& g = L.p[which];
-  const CUtensorMap* tm_ah = which ? &tm_ah1 : &tm_ah0;
-  const CUtensorMap* tm_al = which ? &tm_al1 : &tm_al0;
-  const CUtensorMap* tm_bh = which ? &tm_bh1 : &tm_bh0;
-  const CUtensorMap* tm_bl = which ? &tm_bl1 : &tm_bl0;
-  const int tile = (int)blockIdx.x - (which ? L.tiles0 : 0);
-  const int tile_n = tile % g.tiles_n, tile_m = tile / g.tiles_n;
-  const int m0 = tile_m * kTileQ;
-  const int n0 = tile_n * g.bn;
-  const uint32_t b_bytes = (uint32_t)g.bn * 128u;  // one B box: bn rows x 64 bf16
+  const int pair = (int)blockIdx.x;       // (tile walker: this CTA, stride = grid)
+  const int n_pairs = (int)gridDim.x;
 
-  const uint32_t bar_base = smem_base + (uint32_t)(kGemmStages * kGemmStageBytes);
+  const uint32_t xpose_smem = smem_base + (uint32_t)(kGemmStages * kGemmStageBytes);
+  const uint32_t bar_base = xpose_smem + (uint32_t)kGemmXposeBytes;
   const uint32_t full_bar = bar_base;             // [kGemmStages]
-  const uint32_t empty_bar = bar_base + 64;       // [kGemmStages]
-  const uint32_t tfull_bar = bar_base + 128;      // [1]
-  const uint32_t tmem_ptr_addr = bar_base + 136;
+  const uint32_t empty_bar = bar_base + 32;       // [kGemmStages]
+  const uint32_t tfull_bar = bar_base + 64;       // [2]
+  const uint32_t tempty_bar = bar_base + 80;      // [2]
+  const uint32_t tmem_ptr_addr = bar_base + 96;
   volatile uint32_t* tmem_ptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  float* const xpose = reinterpret_cast<float*>(smem_raw + (xpose_smem - smem_u32(smem_raw)));
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tm_ah);
-    tma_prefetch_desc(tm_al);
-    tma_prefetch_desc(tm_bh);
-    tma_prefetch_desc(tm_bl);
+    tma_prefetch_desc(&tm_ah0);
+    tma_prefetch_desc(&tm_al0);
+    tma_prefetch_desc(&tm_bh0);
+    tma_prefetch_desc(&tm_bl0);
+    if (L.n_problems > 1) {
+      tma_prefetch_desc(&tm_ah1);
+      tma_prefetch_desc(&tm_al1);
+      tma_prefetch_desc(&tm_bh1);
+      tma_prefetch_desc(&tm_bl1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tfull_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -181,130 +169,239 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        mbar_wait(empty_bar + 8 * stage, phase ^ 1u, L.err_flag, 501);
-        mbar_expect_tx(full_bar + 8 * stage, 2u * (uint32_t)kKBlockBytes + 2u * b_bytes);
-        const uint32_t dst = smem_base + (uint32_t)(stage * kGemmStageBytes);
-        tma_load_2d(dst, tm_ah, full_bar + 8 * stage, g.a_k0 + kb * 64, m0);
-        tma_load_2d(dst + kKBlockBytes, tm_al, full_bar + 8 * stage, g.a_k0 + kb * 64, m0);
-        tma_load_2d(dst + 2 * kKBlockBytes, tm_bh, full_bar + 8 * stage, kb * 64, n0);
-        tma_load_2d(dst + 3 * kKBlockBytes, tm_bl, full_bar + 8 * stage, kb * 64, n0);
-        if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+      for (int t = pair; t < L.tiles_total; t += n_pairs) {
+        const TileRef tr = tile_of(L, t);
+        const GemmProblem& g = L.p[tr.which];
+        const CUtensorMap* ah = tr.which ? &tm_ah1 : &tm_ah0;
+        const CUtensorMap* al = tr.which ? &tm_al1 : &tm_al0;
+        const CUtensorMap* bh = tr.which ? &tm_bh1 : &tm_bh0;
+        const CUtensorMap* bl = tr.which ? &tm_bl1 : &tm_bl0;
+        const uint32_t b_bytes = (uint32_t)g.bn * 128u;  // one B box: bn rows x 64 bf16
+        const int my_m = tr.m0, my_n = tr.n0;
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1u, L.err_flag, 501);
+          mbar_expect_tx(full_bar + 8 * stage, 2u * (uint32_t)kKBlockBytes + 2u * b_bytes);
+          const uint32_t dst = smem_base + (uint32_t)(stage * kGemmStageBytes);
+          tma_load_2d(dst, ah, full_bar + 8 * stage, g.a_k0 + kb * 64, my_m);
+          tma_load_2d(dst + kKBlockBytes, al, full_bar + 8 * stage, g.a_k0 + kb * 64, my_m);
+          tma_load_2d(dst + 2 * kKBlockBytes, bh, full_bar + 8 * stage, kb * 64, my_n);
+          tma_load_2d(dst + 3 * kKBlockBytes, bl, full_bar + 8 * stage, kb * 64, my_n);
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-    tc_fence_after();
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < g.num_kb; ++kb) {
-      mbar_wait(full_bar + 8 * stage, phase, L.err_flag, 503);
+    // ===================== MMA issuer (whole warp, one elected lane issues) ======================
+    {
       tc_fence_after();
-      const uint32_t sbase = smem_base + (uint32_t)(stage * kGemmStageBytes);
-      const uint64_t ah = umma_desc_sw128(sbase);
-      const uint64_t al = umma_desc_sw128(sbase + kKBlockBytes);
-      const uint64_t bh = umma_desc_sw128(sbase + 2 * kKBlockBytes);
-      const uint64_t bl = umma_desc_sw128(sbase + 3 * kKBlockBytes);
-      // the last K block may hold fewer than four 16-wide slices of real columns: what follows them in the A buffer
-      // belongs to the next layer's slice and must not enter the product
-      const int n4 = kb + 1 == g.num_kb ? g.last_k4 : 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int t = pair; t < L.tiles_total; t += n_pairs, ++it) {
+        const TileRef tr = tile_of(L, t);
+        const GemmProblem& g = L.p[tr.which];
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
+        const uint32_t slot = it & 1u;
+        mbar_wait(tempty_bar + 8 * slot, ((it >> 1) & 1u) ^ 1u, L.err_flag, 504);  // the accumulator was drained
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * 128u;
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase, L.err_flag, 503);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + (uint32_t)(stage * kGemmStageBytes);
+          const uint64_t ah = umma_desc_sw128(sbase);
+          const uint64_t al = umma_desc_sw128(sbase + kKBlockBytes);
+          const uint64_t bh = umma_desc_sw128(sbase + 2 * kKBlockBytes);
+          const uint64_t bl = umma_desc_sw128(sbase + 3 * kKBlockBytes);
+          // the last K block may hold fewer than four 16-wide slices of real columns: what follows them in the A
+          // buffer belongs to the next layer's slice and must not enter the product
+          const int n4 = kb + 1 == g.num_kb ? g.last_k4 : 4;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        if (k4 < n4) {
-          const uint64_t o = (uint64_t)(2 * k4);
-          // small terms first, the dominant product last (all of them accumulate in fp32 anyway)
-          umma_bf16_n(tmem_base, al + o, bh + o, (kb | k4) != 0 ? 1u : 0u, idesc);
-          umma_bf16_n(tmem_base, ah + o, bl + o, 1u, idesc);
-          umma_bf16_n(tmem_base, ah + o, bh + o, 1u, idesc);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            if (k4 < n4) {
+              const uint64_t o = (uint64_t)(2 * k4);
+              // small terms first, the dominant product last (all of them accumulate in fp32 anyway)
+              umma_bf16_n(d_tmem, al + o, bh + o, (kb | k4) != 0 ? 1u : 0u, idesc);
+              umma_bf16_n(d_tmem, ah + o, bl + o, 1u, idesc);
+              umma_bf16_n(d_tmem, ah + o, bh + o, 1u, idesc);
+            }
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
         }
+        umma_commit(tfull_bar + 8 * slot);
       }
-      umma_commit(empty_bar + 8 * stage);
-      if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
     }
-    umma_commit(tfull_bar);
   } else if (warp >= 4) {
-    // ===================== epilogue: a thread owns one output row =====================
+    // ===================== epilogue (4 warps): TMEM -> registers -> [128][33] transpose -> coalesced global ==========
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < g.M;
-    mbar_wait(tfull_bar, 0, L.err_flag, 505);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    if (g.epi == EPI_GRU) {
-      // tile = 32 hidden units x (r | z | n): columns [0, 32) r, [32, 64) z, [64, 96) n
-      uint32_t rr[32], rz[32], rn[32];
-      tmem_ld32(taddr, rr);
-      tmem_ld32(taddr + 32u, rz);
-      tmem_ld32(taddr + 64u, rn);
-      tmem_ld_wait();
-      if (row_ok) {
-        const int H = g.gru_H;
-        const int u0 = tile_n * 32;
-        const float* ghr = g.gru_gh + (size_t)row * (size_t)g.gru_gh_ld;
-        const float* xr = g.gru_x + (size_t)row * (size_t)g.gru_x_ld;
-        const float* gpr = g.gru_gp + (size_t)row * (size_t)H;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int u = u0 + i;
-          if (u >= H) break;
-          const float ir = __uint_as_float(rr[i]) + g.gru_b_ih[u], iz = __uint_as_float(rz[i]) + g.gru_b_ih[H + u],
-                      in_ = __uint_as_float(rn[i]) + g.gru_b_ih[2 * H + u];
-          const float hr = ghr[u] + g.gru_b_hh[u], hz = ghr[H + u] + g.gru_b_hh[H + u], hn = ghr[2 * H + u] + g.gru_b_hh[2 * H + u];
-          const float rg = 1.0f / (1.0f + expf(-(ir + hr)));
-          const float zg = 1.0f / (1.0f + expf(-(iz + hz)));
-          const float ng = tanhf(in_ + rg * hn);
-          const float x = u < g.gru_in_w ? xr[u] : 0.0f;
-          const float h = (1.0f - zg) * ng + zg * x;
-          const float o = fmaxf(gpr[u] + h, 0.0f);  // HeteroConv sum of the GAT and GatedGraphConv branches, relu
-          g.C[(size_t)row * (size_t)g.ldc + u] = o;
-          store_hilo(g.out_hi, g.out_lo, (size_t)row * g.out_ld + g.out_k0 + u, o);
-        }
-      }
-    } else {
-      float att_partial = 0.0f;
+    const int rl = quarter * 32 + lane;      // phase 1: this thread's row inside the tile
+    const int e = (int)threadIdx.x - 128;    // phase 2: lane = column inside the chunk, e >> 5 = row group
+    const int pc = e & 31, pr = e >> 5;
+    uint32_t it = 0;
+    for (int t = pair; t < L.tiles_total; t += n_pairs, ++it) {
+      const TileRef tr = tile_of(L, t);
+      const GemmProblem& g = L.p[tr.which];
+      const int m0 = tr.m0, n0 = tr.n0, tile_n = tr.tile_n;
+      const uint32_t slot = it & 1u;
+      const int row = m0 + rl;
+      const bool row_ok = row < g.M;
+      const int rows_valid = min(kTileQ, g.M - m0);
+      mbar_wait(tfull_bar + 8 * slot, (it >> 1) & 1u, L.err_flag, 505);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
       const int n_chunks = g.bn / 32;
+      float partial = 0.0f;
+      const float* bc = (g.epi == EPI_ATTPOOL && row_ok) ? g.ap_bc + (size_t)g.ap_node_graph[row] * (size_t)g.N : nullptr;
+      float rg[32], zg[32];  // EPI_GRU: gates of this thread's phase-2 elements (row group k, unit pc)
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        if (g.epi == EPI_STORE) {
-          epi_store(g, row, n0, c, r);
-        } else if (g.epi == EPI_ATT) {
-          // plain fp32 store (16-byte vectors: ldc and n0 are multiples of 128) + the tile's share of <C[row, part], att>
-          float* crow = g.C + (size_t)row * (size_t)g.ldc + n0 + c * 32;
+        if (c + 1 == n_chunks) {  // the accumulator has left TMEM: hand the slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);
+        }
+        if (g.epi == EPI_ATTPOOL) {
+          if (row_ok) {
+            const int col0 = n0 + c * 32;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<uint4*>(crow)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-          const int part = tile_n / g.att_tiles_per_part;
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              if (col < g.N) partial += g.ap_w[col] * fast_sigmoid(__uint_as_float(r[i]) + g.bias[col] + bc[col]);
+            }
+          }
+          continue;
+        }
+        if (g.epi == EPI_ATT) {
+          // attention logits: one partial per (row, 128-column sub-tile); a sub-tile lies inside one part
+          const int sub = (n0 + c * 32) / 128;                 // 128-column sub-tile of the whole output
+          const int part = sub / g.att_tiles_per_part;
           const float* att = part < 4 ? g.att[part] : nullptr;
           if (att != nullptr) {
-            const int pc0 = (tile_n - part * g.att_tiles_per_part) * 128 + c * 32;  // column inside the part
+            const int pc0 = (sub - part * g.att_tiles_per_part) * 128 + (c & 3) * 32;  // column inside the part
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (pc0 + i < g.att_width) att_partial = fmaf(__uint_as_float(r[i]), att[pc0 + i], att_partial);
+              if (pc0 + i < g.att_width) partial = fmaf(__uint_as_float(r[i]), att[pc0 + i], partial);
+            if ((c & 3) == 3) {
+              if (row_ok) g.att_out[part][(size_t)row * g.att_tiles_per_part + (sub - part * g.att_tiles_per_part)] = partial;
+              partial = 0.0f;
+            }
+          }
+        }
+        epi_bar();  // the previous chunk's readers are done with the transpose buffer
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xpose[rl * kGemmXposePitch + i] = __uint_as_float(r[i]);
+        epi_bar();
+        // ---- phase 2: element (row group k -> row 4k + pr, column pc of this chunk)
+        if (g.epi == EPI_STORE || g.epi == EPI_ATT) {
+          const int col = n0 + c * 32 + pc;
+          if (col < g.N) {
+            const float bias = g.bias ? g.bias[col] : 0.0f;
+            for (int k = 0; 4 * k + pr < rows_valid; ++k) {
+              const int rr = 4 * k + pr;
+              float v = xpose[rr * kGemmXposePitch + pc] + bias;
+              if (g.sign_out) {
+                const float sg = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);
+                const float th = tanhf(v);
+                v = (sg - th) + th;  // (sign - tanh).detach() + tanh, model/model.py:137
+              }
+              g.C[(size_t)(m0 + rr) * (size_t)g.ldc + col] = v;
+            }
+          }
+        } else if (g.epi == EPI_GRU) {
+          // every 96 columns = 32 hidden units x (r | z | n): chunk c -> unit group c / 3, gate c % 3; lane = unit
+          const int H = g.gru_H;
+          const int gate = c % 3;
+          const int u = (tile_n * (g.bn / 96) + c / 3) * 32 + pc;
+          if (u < H) {
+            const float bi = g.gru_b_ih[gate * H + u], bh = g.gru_b_hh[gate * H + u];
+            // all global operands of the chunk are requested before the first one is used: 32 independent loads in
+            // flight per thread instead of 32 serialised L2 round trips (160 us per launch that way)
+            const float* ghp = g.gru_gh + (size_t)(m0 + pr) * (size_t)g.gru_gh_ld + gate * H + u;
+            const size_t gh_step = 4 * (size_t)g.gru_gh_ld;
+            float ghv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ghv[k] = 4 * k + pr < rows_valid ? __ldg(ghp + k * gh_step) : 0.0f;
+            if (gate < 2) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float gi = xpose[(4 * k + pr) * kGemmXposePitch + pc] + bi;
+                const float sgm = fast_sigmoid(gi + ghv[k] + bh);
+                if (gate == 0) rg[k] = sgm; else zg[k] = sgm;
+              }
+            } else {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                float xv[16], gpv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int rr = 4 * (16 * half + j) + pr;
+                  const bool ok = rr < rows_valid;
+                  xv[j] = (ok && u < g.gru_in_w) ? __ldg(g.gru_x + (size_t)(m0 + rr) * (size_t)g.gru_x_ld + u) : 0.0f;
+                  gpv[j] = ok ? __ldg(g.gru_gp + (size_t)(m0 + rr) * (size_t)H + u) : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int k = 16 * half + j;
+                  const int rr = 4 * k + pr;
+                  if (rr < rows_valid) {
+                    const float gi = xpose[rr * kGemmXposePitch + pc] + bi;
+                    const float ng = fast_tanh(gi + rg[k] * (ghv[k] + bh));
+                    const float h = (1.0f - zg[k]) * ng + zg[k] * xv[j];
+                    const float o = fmaxf(gpv[j] + h, 0.0f);  // HeteroConv sum of both branches, relu
+                    g.C[(size_t)(m0 + rr) * (size_t)g.ldc + u] = o;
+                    store_hilo(g.out_hi, g.out_lo, (size_t)(m0 + rr) * g.out_ld + g.out_k0 + u, o);
+                  }
+                }
+              }
+            }
           }
         } else if (g.epi == EPI_POOL) {
-          epi_pool(g, row, n0, c, r);
-        } else {  // EPI_ATTPOOL
-          const int col0 = n0 + c * 32;
-          const float* bc = g.ap_bc + (size_t)g.ap_node_graph[row] * (size_t)g.N;
+          const int W = g.pool_lin_w + g.pool_msl;
+          const int col = n0 + c * 32 + pc;
+          if (col < W) {
+            const bool is_lin = col < g.pool_lin_w;
+            const float bias = is_lin ? g.bias[col] : 0.0f;
+            // output rows of an input row: a query -> one row after the product occurrences; a product -> one per
+            // occurrence (repeat_interleave by cnt).  Row ranges first (independent loads), then the stores.
+            int t0v[32], t1v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = col0 + i;
-            if (col < g.N)
-              att_partial += g.ap_w[col] * (1.0f / (1.0f + expf(-(__uint_as_float(r[i]) + g.bias[col] + bc[col]))));
+            for (int k = 0; k < 32; ++k) {
+              const int rr = 4 * k + pr;
+              const int grow = m0 + rr;
+              t0v[k] = 0;
+              t1v[k] = 0;
+              if (rr < rows_valid) {
+                if (g.pool_is_product) {
+                  t0v[k] = __ldg(g.pool_prefix + grow);
+                  t1v[k] = __ldg(g.pool_prefix + grow + 1);
+                } else {
+                  t0v[k] = g.pool_row0 + grow;
+                  t1v[k] = t0v[k] + 1;
+                }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int rr = 4 * k + pr;
+              const float lin = is_lin ? fast_tanh(xpose[rr * kGemmXposePitch + pc] + bias) : 0.0f;
+              for (int tt = t0v[k]; tt < t1v[k]; ++tt) {
+                float x = lin;
+                if (!is_lin) {
+                  const int64_t pos = g.pool_pos[g.pool_is_product ? tt : m0 + rr];
+                  x = fast_tanh(g.pool_pe[pos * g.pool_msl + (col - g.pool_lin_w)]);
+                }
+                g.pool_U[(size_t)tt * W + col] = x;
+                store_hilo(g.out_hi, g.out_lo, (size_t)tt * g.out_ld + col, x);
+              }
+            }
           }
         }
       }
-      if (row_ok && g.epi == EPI_ATT) {
-        const int part = tile_n / g.att_tiles_per_part;
-        if (part < 4 && g.att[part] != nullptr)
-          g.att_out[part][(size_t)row * g.att_tiles_per_part + (tile_n - part * g.att_tiles_per_part)] = att_partial;
-      }
-      if (row_ok && g.epi == EPI_ATTPOOL) g.ap_out[(size_t)row * g.tiles_n + tile_n] = att_partial;
+      if (row_ok && g.epi == EPI_ATTPOOL) g.ap_out[(size_t)row * g.tiles_n + tile_n] = partial;
     }
   }
 
@@ -360,6 +457,7 @@ int launch_gemm_bf16x3(const GemmProblem* problems, int n_problems, int* err_fla
     SSS_REQUIRE(g.num_kb >= 1 && g.last_k4 >= 1 && g.last_k4 <= 4 && g.tiles_n >= 1, "gemm_bf16x3: bad K / N tiling");
     SSS_REQUIRE(g.a_rows_pad % 128 == 0 && g.a_ld % 64 == 0 && g.b_ld % 64 == 0, "gemm_bf16x3: bad operand pitch");
     SSS_REQUIRE((g.a_k0 * 2) % 16 == 0, "gemm_bf16x3: A column offset must be 16-byte aligned");
+    SSS_REQUIRE(g.b_rows_pad >= g.tiles_n * g.bn, "gemm_bf16x3: the weight operand must be padded to whole tiles");
     if (make_tensor_map_bf16_2d(tm[4 * i + 0], g.a_hi, (uint64_t)g.a_rows_pad, (uint64_t)g.a_ld, 128)) return 1;
     if (make_tensor_map_bf16_2d(tm[4 * i + 1], g.a_lo, (uint64_t)g.a_rows_pad, (uint64_t)g.a_ld, 128)) return 1;
     if (make_tensor_map_bf16_2d(tm[4 * i + 2], g.b_hi, (uint64_t)g.b_rows_pad, (uint64_t)g.b_ld, (uint32_t)g.bn)) return 1;
@@ -371,10 +469,19 @@ int launch_gemm_bf16x3(const GemmProblem* problems, int n_problems, int* err_fla
   L.tiles0 = tiles[0];
   L.err_flag = err_flag;
   const int total = tiles[0] + tiles[1];
+  L.tiles_total = total;
   if (total <= 0) return 0;
   static SmemAttr attr;  // per device
   if (attr.ensure(gemm_bf16x3_kernel, kGemmSmemBytes)) return 1;
-  gemm_bf16x3_kernel<<<(unsigned)total, kGemmThreads, kGemmSmemBytes, stream>>>(
+  int dev = 0, n_sm = 148;
+  SSS_CUDA_OK(cudaGetDevice(&dev));
+  static int sm_count[64] = {0};
+  if (dev >= 0 && dev < 64) {
+    if (!sm_count[dev]) SSS_CUDA_OK(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    n_sm = sm_count[dev];
+  }
+  const int grid = total < n_sm ? total : n_sm;  // persistent: one CTA per SM walks the tiles
+  gemm_bf16x3_kernel<<<(unsigned)grid, kGemmThreads, kGemmSmemBytes, stream>>>(
       *(const CUtensorMap*)tm[0], *(const CUtensorMap*)tm[1], *(const CUtensorMap*)tm[2], *(const CUtensorMap*)tm[3],
       *(const CUtensorMap*)tm[4], *(const CUtensorMap*)tm[5], *(const CUtensorMap*)tm[6], *(const CUtensorMap*)tm[7], L);
   SSS_CUDA_OK(cudaGetLastError());

@@ -473,30 +473,6 @@ scan_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_db, const ScanParam
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");  // (not .aligned: single-lane roles reach it diverged)
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  // default semantics (release at CTA scope): the slot hand-off orders TMEM reads through the tcgen05 fences, and a
-  // cluster-scope release compiles to MEMBAR.ALL.GPU in front of every arrive (1-2 us under a saturated HBM stream)
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\t"
@@ -516,14 +492,6 @@ __device__ __forceinline__ void umma_fp8_2cta(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc2Fp8), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(bar), "h"((uint16_t)3)
-      : "memory");
-}
-
 template <int kCap, bool kFp8>  // records per private sub-region (compile time: the epilogue is sensitive to it)
 __global__ void __launch_bounds__(kNumThreads, 1)
 scan_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
