@@ -664,8 +664,16 @@ def run_e2e(env, a):
             "query_sessions_per_s_end_to_end": n / t_query, "query_path_s": t_query,
             "query_path": "flatten + native featuriser + encoder (data-parallel) + all-gather of embeddings + "
                           "row-sharded K-loop search + merge; wall clock, max over ranks",
-            "encoder_ms_per_batch_200": enc_ms, "encoder_sessions_per_s_per_gpu": 200.0 / (enc_ms * 1e-3),
-            "encoder_tflops": fl / (enc_ms * 1e-3) / 1e12, "encoder_flop_per_batch": fl,
+            "encoder": {"ms_per_batch_200": enc_ms, "sessions_per_s_per_gpu": 200.0 / (enc_ms * 1e-3),
+                        "launches_per_forward": enc.launches, "flop_per_batch": fl,
+                        "algorithmic_tflops": fl / (enc_ms * 1e-3) / 1e12,
+                        "issued_bf16_tflops": 3.0 * fl / (enc_ms * 1e-3) / 1e12,
+                        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": 3.0 * fl / (enc_ms * 1e-3) / 1e12,
+                                     "peak": float(measured_peaks()[0].get("bf16_tflops", 1660.3)),
+                                     "frac": 3.0 * fl / (enc_ms * 1e-3) / 1e12 / float(measured_peaks()[0].get("bf16_tflops", 1660.3)),
+                                     "note": "three bf16 products per fp32-accurate multiply (split-bf16 GEMM); the forward "
+                                             "is bound by operand-stream latency at batch 200, not by the tensor pipe "
+                                             "(profiles/r02_encoder.md)"}},
             "own_session_first": float(own.mean()), "parity": parity}
 
 

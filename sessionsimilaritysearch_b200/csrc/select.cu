@@ -631,40 +631,43 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
 
 // ---- bootstrap thresholds ---------------------------------------------------------------------------------
 // A tensor-core pass in chunk-max mode left cmax[chunk, q] = max score of 32 consecutive rows.  Among the
-// (k-1) * gap + 1 largest chunk maxima of a query one can pick k chunks that are pairwise >= gap chunks apart,
+// (k-1) * gap + 1 largest chunk maxima of a query one can pick k chunks that are pairwise >= gap chunks apart
+// (the kernel below looks at every gap-th chunk only, where any k chunks are),
 // i.e. (with gap = floor((max session length + 30) / 32) + 1, or 1 without sessions) k rows of k DISTINCT
 // sessions/rows whose scores are >= T, the smallest of those maxima.  So the k-th best exact session score is >= T - margin and a row
 // can only matter if its tensor-core score is >= T - 2 * margin: thr = the float just below that.
-// One block = 8 consecutive queries: the chunk maxima are stored [chunk][query], so 8 threads read one full 32-byte
-// sector per chunk (a block per query read 4 of every 32 bytes it pulled: 128 MB of L2 traffic per 1000 queries).
-// Warp w then finds the need-th largest key of query w by a bitwise binary search from the top bit down — 32 counting
-// passes over its 4096 keys in shared memory, no atomics (a radix select's histogram serialises here: the maxima of
-// one query share their leading bits, so a whole warp hits two or three bins).
+// Only every gap-th chunk is looked at: any k of those are pairwise >= gap chunks apart, so the k-th largest of them
+// is the threshold directly (the same quantile as the ((k-1) * gap + 1)-th largest of all chunks, from 1 / gap of the
+// keys).  One block = 8 consecutive queries: the chunk maxima are stored [chunk][query], so 8 threads read one full
+// 32-byte sector per chunk (a block per query read 4 of every 32 bytes it pulled: 128 MB of L2 traffic per 1000
+// queries).  Warp w then finds the k-th largest key of query w by a bitwise binary search from the first bit in which
+// the keys differ down to bit 8 — counting passes over shared memory, no atomics (a radix select's histogram
+// serialises here: the maxima of one query share their leading bits, so a whole warp hits two or three bins).
 constexpr int kBootQ = 8;
 __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restrict__ cmax, int n_chunks, int64_t nq,
                                                             int64_t nq_pad, int k, int chunk_gap, float slack_mult,
                                                             SelectState st) {
-  extern __shared__ uint32_t bs_keys[];  // [kBootQ][n_chunks + 8] (row pitch keeps the transposing stores conflict free)
-  const int pitch = n_chunks + 8;
+  extern __shared__ uint32_t bs_keys[];  // [kBootQ][n_s + 8] (row pitch keeps the transposing stores conflict free)
+  const int n_s = n_chunks / chunk_gap;  // sampled chunks: 0, gap, 2 gap, ...
+  const int pitch = n_s + 8;
   const int64_t q0 = (int64_t)blockIdx.x * kBootQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // of the `need` largest chunks, taken in index order, every gap-th one is >= gap chunks from the previous pick
-  const int need = (k - 1) * chunk_gap + 1;
-  if (need > n_chunks) return;
+  const int need = k;
+  if (need > n_s) return;
   {
     // 16 independent loads in flight per thread: with a handful of blocks (few queries) this phase is pure latency
     const int qq = tid & 7;
-    for (int i0 = tid >> 3; i0 < n_chunks; i0 += 32 * 16) {
+    for (int i0 = tid >> 3; i0 < n_s; i0 += 32 * 16) {
       float v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int i = i0 + 32 * u;
-        v[u] = i < n_chunks ? cmax[(size_t)i * (size_t)nq_pad + (size_t)(q0 + qq)] : 0.0f;
+        v[u] = i < n_s ? cmax[(size_t)i * (size_t)chunk_gap * (size_t)nq_pad + (size_t)(q0 + qq)] : 0.0f;
       }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int i = i0 + 32 * u;
-        if (i < n_chunks) bs_keys[qq * pitch + i] = score_key(v[u]);
+        if (i < n_s) bs_keys[qq * pitch + i] = score_key(v[u]);
       }
     }
   }
@@ -675,17 +678,21 @@ __global__ void __launch_bounds__(256) bootstrap_thr_kernel(const float* __restr
   // bits above the highest one in which the keys differ are common to all of them
   uint32_t diff = 0u;
   const uint32_t k0 = keys[0];
-  for (int i = lane; i < n_chunks; i += 32) diff |= keys[i] ^ k0;
+  for (int i = lane; i < n_s; i += 32) diff |= keys[i] ^ k0;
   diff = __reduce_or_sync(0xffffffffu, diff);
   const int top = diff ? 31 - __clz(diff) : -1;
-  // largest v (low 8 bits left zero: any lower bound of the need-th largest key is a valid threshold, and 2^-15
-  // relative is far inside the slack) with count(keys >= v) >= need, built bit by bit
+  // largest v (low 8 bits left zero: any lower bound of the k-th largest key is a valid threshold, and 2^-15
+  // relative is far inside the slack) with count(keys >= v) >= k, built bit by bit
   uint32_t prefix = top >= 31 ? 0u : (k0 & ~((2u << top) - 1u));
   if (top < 0) prefix = k0;
   for (int bit = top; bit >= 8; --bit) {
     const uint32_t cand = prefix | (1u << bit);
     int cnt = 0;
-    for (int i = lane; i < n_chunks; i += 32) cnt += keys[i] >= cand ? 1 : 0;
+    int i = lane;
+    for (; i + 96 < n_s; i += 128)
+      cnt += (keys[i] >= cand ? 1 : 0) + (keys[i + 32] >= cand ? 1 : 0) + (keys[i + 64] >= cand ? 1 : 0) +
+             (keys[i + 96] >= cand ? 1 : 0);
+    for (; i < n_s; i += 32) cnt += keys[i] >= cand ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (cnt >= need) prefix = cand;
   }
