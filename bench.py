@@ -5,7 +5,7 @@ blocks of the same JSON line (configs[3]: 100M rows sharded; configs[4]: session
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
     python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
-    python bench.py --configs headline                        # headline only (default: headline,100m,e2e)
+    python bench.py --configs headline                        # headline only (default: headline,1m,100m,e2e,binary)
 
 A "step" answers one batch of nq=1000 query sessions against the whole database and returns the top-100
 sessions per query; every step uses a different query batch, whose targets are spread over all shards.  With N>1
@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--reduce", default="max", choices=["max", "sum", "none"])
     ap.add_argument("--metric", default="cos", choices=["cos", "l2"],
                     help="cos = the headline (inner product over normalised rows); l2 = squared L2 over the same rows")
-    ap.add_argument("--configs", default="headline,100m,e2e",
-                    help="comma list of: headline (always run), 100m (configs[3]), e2e (configs[4]), binary (Hamming)")
+    ap.add_argument("--configs", default="headline,1m,100m,e2e,binary",
+                    help="comma list of: headline (always run), 1m (configs[1]), 100m (configs[3]), e2e (configs[4]), "
+                         "binary (Hamming search, N = 1 only)")
     ap.add_argument("--rows-100m", type=int, default=100_000_000)
     ap.add_argument("--e2e-sessions", type=int, default=100_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=10_000_000,
@@ -633,6 +634,9 @@ def run_e2e(env, a):
     enc_ms = e0.elapsed_time(e1) / 20
     # parity of the wide-row (K-loop) shard search against the oracle on this rank's own rows
     parity = None
+    qe_par = None
+    if not a.no_parity:  # (a collective when world > 1: every rank takes part, rank 0 uses the result)
+        qe_par = sss.normalize(pipe.encode_queries(queries[:8 * env.world])[:8].contiguous())
     if not a.no_parity and env.rank == 0:
         from oracle import search_oracle as so
         inner = pipe.index.inner if env.world > 1 else pipe.index
@@ -642,7 +646,7 @@ def run_e2e(env, a):
         small = sss.IndexFlatIP(out_dim, device=env.local_rank, mode=a.mode)
         small.add(emb, norm=sss.NORM_UTIL)
         small.set_segments(seg, "max")
-        qe = sss.normalize(pipe.encode_queries(queries[:8 * env.world])[:8].contiguous())
+        qe = qe_par
         Ds, Is = small.search(qe, a.k)
         Do, Io = so.search_flat(so.normalize(emb.cpu().numpy(), so.NORM_UTIL), qe.cpu().numpy(), a.k, seg_off=seg,
                                 reduce=so.REDUCE_MAX)
@@ -651,8 +655,6 @@ def run_e2e(env, a):
                   "checked": "8 queries x %d encoded subsession rows x 1600 of rank 0 (K-loop tensor scan + fp32 "
                              "re-score) against oracle O2, ids and scores bit for bit" % int(seg[-1]),
                   "own_session_first": float(own.mean())}
-    if env.world > 1:
-        pipe.encode_queries(queries[:env.world])  # keep the collective sequence identical on every rank
     tm = pipe.timings
     return {"workload": "configs[4]: %d sessions -> %d subsession rows x 1600 (session max), %d query sessions "
                         "(2/3 prefixes), top-%d sessions; encoder 768 -> 3 x 800 -> 3168 -> 1600, batches of 200"
@@ -695,6 +697,21 @@ def main():
     failures = []
     if res["parity"] is not None and not res["parity"]["ok"]:
         failures.append("headline parity")
+    if "1m" in configs and world == 1:
+        try:  # configs[1]: 1M session embeddings, 1k query batch, cosine top-100, GEMM + top-k only (no session reduce)
+            import copy
+            a1 = copy.copy(a)
+            a1.reduce = "none"
+            r1 = run_search_config(env, a1, 1_000_000, max(2, min(a.steps, 10)), 3, "configs[1]", False, False)
+            peaks, peak_kind = measured_peaks()
+            blocks["1m"] = {"workload": workload_config(a1, 1_000_000, world, "configs[1]")["workload"],
+                            "value": r1["value"], "unit": "queries/s", "ms_per_step": r1["ms_per_step"],
+                            "e2e_value": r1["e2e_value"], "waves": r1["waves"],
+                            "roofline": roofline_of(a1, r1, r1["rows_local"], peaks, peak_kind), "parity": r1["parity"]}
+            if r1["parity"] is not None and not r1["parity"]["ok"]:
+                failures.append("1m parity")
+        except Exception as e:
+            blocks["1m"] = {"error": str(e)[:300]}
     if "100m" in configs:
         try:
             steps_b = max(2, min(a.steps, 5))
@@ -763,11 +780,62 @@ def main():
         sys.exit(1)
 
 
-def run_binary(env, a):
-    """Hamming top-k over 256-bit codes (what fine_tune_ours.test() executes, code_len 250 -> 256
-    bits): HBM-bound code stream; filled in by the binary benchmark leg."""
-    from sessionsimilaritysearch_b200 import binary_bench
-    return binary_bench.run(env, a)
+def run_binary(env, a, rows=None, nq_list=(1000, 128, 1), k=100):
+    """Hamming top-k over 256-bit codes (what fine_tune_ours.test() executes as committed: code_len 250
+    -> 256-bit codes -> faiss.IndexBinaryFlat, fine_tune_ours.py:826,839-843,871-876): +-1 E4M3 tensor-core scan."""
+    import sessionsimilaritysearch_b200 as sss
+    torch = env.torch
+    rows = int(rows or a.rows_100m)
+    nbits, nbytes = 256, 32
+    g = torch.Generator(device=env.dev).manual_seed(7)
+    ix = sss.IndexBinaryFlat(nbits, device=env.local_rank)
+    pool = None
+    for lo in range(0, rows, 4_000_000):
+        n = min(4_000_000, rows - lo)
+        c = torch.randint(0, 256, (n, nbytes), generator=g, device=env.dev, dtype=torch.uint8)
+        if pool is None:
+            pool = c[:4096].clone()
+        ix.add(c)
+        del c
+    out = {"workload": "%d codes x %d bit (IndexBinaryFlat), top-%d, queries = database codes with 8%% of the bits "
+                       "flipped" % (rows, nbits, k), "rows": rows}
+    peaks_hbm = None
+    for nq in nq_list:
+        flip = (torch.rand((nq, nbytes, 8), generator=g, device=env.dev) < 0.08)
+        w = (2 ** torch.arange(7, -1, -1, device=env.dev)).to(torch.int32)
+        q = pool[:nq] ^ (flip.to(torch.int32) * w).sum(-1).to(torch.uint8)
+        for _ in range(3):
+            D, I = ix.search(q, k)
+        ms = env.timed(lambda i: ix.search(q, k), 5) / 5
+        st = ix.stats()
+        ix.set_profiling(True)
+        ix.search(q, k)
+        sp = ix.stats()
+        ix.set_profiling(False)
+        tensor = st["scan_variant"] in ("ts", "2cta")
+        row_bytes = 256 if tensor else nbytes
+        blk = {"ms_per_search": ms, "queries_per_s": nq / (ms * 1e-3), "scan_variant": st["scan_variant"],
+               "waves": st["waves"], "graph_replay": bool(st["graph"]),
+               "scan_kernel_ms": sp["scan_ns"] * 1e-6,
+               "db_stream_gbs_as_stored": rows * row_bytes / (ms * 1e-3) / 1e9,
+               "db_stream_gbs_packed_equivalent": rows * nbytes / (ms * 1e-3) / 1e9,
+               "pairs_per_s": nq * rows / (ms * 1e-3),
+               "tensor_tflops_fp8": (2.0 * nq * rows * nbits / (ms * 1e-3) / 1e12) if tensor else None}
+        # parity on a sample: the popcount oracle over the first 2M codes against a 2M-code index
+        out["nq%d" % nq] = blk
+    if env.rank == 0 and not a.no_parity:
+        from oracle import search_oracle as so
+        n_s = min(rows, 2_000_000)
+        gs = torch.Generator(device=env.dev).manual_seed(7)
+        c = torch.randint(0, 256, (min(4_000_000, rows), nbytes), generator=gs, device=env.dev, dtype=torch.uint8)[:n_s]
+        small = sss.IndexBinaryFlat(nbits, device=env.local_rank)
+        small.add(c)
+        q = pool[:64] ^ 1
+        Ds, Is = small.search(q, k)
+        Do, Io = so.search_hamming(c.cpu().numpy(), q.cpu().numpy(), k)
+        out["parity"] = {"ok": bool(np.array_equal(Ds.cpu().numpy(), Do) and np.array_equal(Is.cpu().numpy(), Io)),
+                         "checked": "64 queries x %d codes against the popcount oracle, distances and ids" % n_s}
+    return out
 
 
 if __name__ == "__main__":

@@ -104,11 +104,16 @@ int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int k, int mod
                      float* D, int64_t* I, int out_on_device, void* stream);
 
 /* Top-k search of one row shard for the sharded path: the same search, results written as ONE packed device block
- * [ids int64 nq*k | scores fp32 nq*k] of sss_packed_bytes(nq, k) bytes — the unit every rank contributes to the
- * single all-gather; sss_topk_merge_packed consumes the gathered blocks as they are. */
+ * [ids int64 nq*k | scores fp32 nq*k | pad | 16-byte trailer: int32 status] of sss_packed_bytes(nq, k) bytes — the
+ * unit every rank contributes to the single all-gather; sss_topk_merge_packed consumes the gathered
+ * blocks as they are.  async = 0: like sss_index_search (status read back, overflow re-run inside the call).
+ * async = 1: nothing is read back and the call returns as soon as the work is enqueued; the search's status word
+ * travels in the trailer, sss_topk_merge_packed ORs the trailers of all shards into *status_out, and a caller that
+ * finds it non-zero (on every rank alike, since all ranks merge the same blocks) repeats the search with async = 0.
+ * That removes the one host round trip in the middle of the sharded step. */
 int64_t sss_packed_bytes(int64_t nq, int k);
 int sss_index_search_packed(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
-                            void* packed, void* stream);
+                            void* packed, int async, void* stream);
 
 /* Counters of the last search on this handle.  what: 0 = kernels launched, 1 = scan waves,
  * 2 = overflow reruns, 3 = scan-kernel device time in ns, 4 = scan-kernel launches, 5..8 = refine volumes
@@ -133,7 +138,7 @@ int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_shards, int
 /* The same merge over n_shards packed blocks laid end to end (the output of all-gathering sss_index_search_packed
  * blocks).  Limit of both forms: n_shards * k <= 8192 (one shared-memory sort per query). */
 int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k, int metric, float* D, int64_t* I,
-                          int device, void* stream);
+                          int* status_out /* device int32, may be NULL */, int device, void* stream);
 
 /* ---- binary index (replaces faiss.IndexBinaryFlat, fine_tune_ours.py:839-843,871-876) ------------ */
 

@@ -65,8 +65,8 @@ SIGNATURES = {
     "sss_index_dim": (c_int, [c_vp]),
     "sss_index_search": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "sss_packed_bytes": (c_i64, [c_i64, c_int]),
-    "sss_index_search_packed": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
-    "sss_topk_merge_packed": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "sss_index_search_packed": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "sss_topk_merge_packed": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
     "sss_index_stat": (c_i64, [c_vp, c_int]),
     "sss_index_set_profiling": (c_int, [c_vp, c_int]),
     "sss_normalize": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),

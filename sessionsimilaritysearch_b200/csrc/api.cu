@@ -495,6 +495,7 @@ struct BatchArgs {
   bool q_on_device, out_on_device;
   float* D;
   int64_t* I;
+  int* status_out = nullptr;  // asynchronous form: no status read-back, no re-run; emit ORs the status word in here
 };
 
 // Everything a search pass needs that does not depend on the attempt: operands, plan, tensor maps.
@@ -520,8 +521,8 @@ static int replan(sss_index* ix, SearchCtx& c) {
 
 // Enqueue one whole search on `st`: query staging, bootstrap thresholds, scan + refine waves, emit.  No allocation and
 // no synchronisation in here (it is what gets captured into a graph); `profile` adds CUDA events around the scans.
-static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev, bool safe,
-                          bool profile, cudaStream_t st) {
+static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev, int* status_out,
+                          bool safe, bool profile, cudaStream_t st) {
   Workspace& ws = ix->ws;
   RowStore& rs = *c.rs;
   const int64_t n_rows = c.n_rows;
@@ -622,7 +623,7 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
   }
   if (ix->binary) {
     if (launch_emit_hamming(state, c.nq, c.k, tensor ? ix->b_nbits : 0, ix->id_offset, (int32_t*)Ddev, Idev, st)) return 1;
-  } else if (launch_emit(state, c.nq, c.k, ix->metric, ix->id_offset, Ddev, Idev, st)) {
+  } else if (launch_emit(state, c.nq, c.k, ix->metric, ix->id_offset, Ddev, Idev, status_out, st)) {
     return 1;
   }
   c.kernels += 1;
@@ -651,7 +652,7 @@ static int find_graph_nodes(SearchGraph& g, bool binary) {
 
 // re-bind pointer arguments of one kernel node: (argument index, new value) pairs
 static int rebind(SearchGraph& g, cudaGraphNode_t node, int n_args, int i0, const void* v0, int i1 = -1,
-                  const void* v1 = nullptr) {
+                  const void* v1 = nullptr, int i2 = -1, const void* v2 = nullptr) {
   cudaKernelNodeParams kp;
   SSS_CUDA_OK(cudaGraphKernelNodeGetParams(node, &kp));
   SSS_REQUIRE(kp.kernelParams != nullptr && n_args <= 16, "captured kernel node exposes no parameter array");
@@ -659,13 +660,15 @@ static int rebind(SearchGraph& g, cudaGraphNode_t node, int n_args, int i0, cons
   for (int i = 0; i < n_args; ++i) args[i] = kp.kernelParams[i];
   args[i0] = (void*)&v0;
   if (i1 >= 0) args[i1] = (void*)&v1;
+  if (i2 >= 0) args[i2] = (void*)&v2;
   kp.kernelParams = args;
   kp.extra = nullptr;
   SSS_CUDA_OK(cudaGraphExecKernelNodeSetParams(g.exec, node, &kp));
   return 0;
 }
 
-static SearchGraph* capture_graph(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev) {
+static SearchGraph* capture_graph(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev,
+                                  int* status_out) {
   if (!ix->cap_stream && cudaStreamCreateWithFlags(&ix->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
   SearchGraph g;
   g.nq = c.nq;
@@ -677,7 +680,7 @@ static SearchGraph* capture_graph(sss_index* ix, SearchCtx& c, const float* q_in
     cudaGetLastError();
     return nullptr;
   }
-  const int rc = enqueue_search(ix, c, q_in, Ddev, Idev, false, false, ix->cap_stream);
+  const int rc = enqueue_search(ix, c, q_in, Ddev, Idev, status_out, false, false, ix->cap_stream);
   cudaError_t e = cudaStreamEndCapture(ix->cap_stream, &g.graph);
   if (rc != 0 || e != cudaSuccess || g.graph == nullptr) {
     cudaGetLastError();
@@ -759,8 +762,9 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         if (cand.nq == c.nq && cand.k == c.k && cand.mode == c.mode && cand.epoch == ix->epoch &&
             cand.ws_gen == ws.generation)
           g = &cand;
-      if (!g) g = capture_graph(ix, c, qdev, Ddev, Idev);
-      if (g && rebind(*g, g->prep, ix->binary ? 8 : 11, 0, qdev) == 0 && rebind(*g, g->emit, 7, 5, Ddev, 6, Idev) == 0 &&
+      if (!g) g = capture_graph(ix, c, qdev, Ddev, Idev, b.status_out);
+      if (g && rebind(*g, g->prep, ix->binary ? 8 : 11, 0, qdev) == 0 &&
+          rebind(*g, g->emit, ix->binary ? 7 : 8, 5, Ddev, 6, Idev, ix->binary ? -1 : 7, b.status_out) == 0 &&
           cudaGraphLaunch(g->exec, st) == cudaSuccess) {
         g->last_use = ++ix->graph_clock;
         c.kernels = g->kernels;
@@ -771,9 +775,10 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         cudaGetLastError();  // graphs are an optimisation: anything unexpected falls back to plain launches
       }
     }
-    if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, safe, ix->profile, st)) return 1;
+    if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, b.status_out, safe, ix->profile, st)) return 1;
     ix->stat_kernels += c.kernels;
     ix->stat_waves += c.waves;
+    if (b.status_out != nullptr) return 0;  // asynchronous form: the caller reads the status word when it suits it
     SSS_CUDA_OK(cudaMemcpyAsync(ws.host_flags, ws.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!b.out_on_device) {
       SSS_CUDA_OK(cudaMemcpyAsync(b.D, Ddev, (size_t)b.nq * b.k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -811,7 +816,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
 }
 
 static int search_all(sss_index* ix, const float* q, int64_t nq, int k, int mode, int q_on_device, float* D, int64_t* I,
-                      int out_on_device, void* stream, const char* who) {
+                      int out_on_device, void* stream, const char* who, int* status_out = nullptr) {
   SSS_REQUIRE(ix != nullptr, std::string(who) + ": NULL index");
   SSS_REQUIRE(k >= 1, std::string(who) + ": k must be >= 1");
   SSS_REQUIRE(nq >= 0, std::string(who) + ": negative nq");
@@ -835,6 +840,7 @@ static int search_all(sss_index* ix, const float* q, int64_t nq, int k, int mode
     b.out_on_device = out_on_device != 0;
     b.D = D + q0 * k;
     b.I = I + q0 * k;
+    b.status_out = status_out;
     if (search_batch(ix, b, st)) return 1;
   }
   return 0;
@@ -849,14 +855,21 @@ extern "C" int sss_index_search(sss_index_t* ix, const float* q, int64_t nq, int
 
 // Bytes of one rank's packed candidate block [ids int64 nq*k | scores fp32 nq*k], padded to 16 bytes: the unit of
 // the sharded search's single all-gather.
-extern "C" int64_t sss_packed_bytes(int64_t nq, int k) { return (nq * k * 12 + 15) / 16 * 16; }
+// + 16 bytes of trailer: [int32 status | 12 bytes pad]
+extern "C" int64_t sss_packed_bytes(int64_t nq, int k) { return (nq * k * 12 + 15) / 16 * 16 + 16; }
 
 extern "C" int sss_index_search_packed(sss_index_t* ix, const float* q, int64_t nq, int k, int mode, int q_on_device,
-                                       void* packed, void* stream) {
+                                       void* packed, int async, void* stream) {
   SSS_REQUIRE(packed != nullptr, "sss_index_search_packed: NULL buffer");
+  SSS_REQUIRE(nq >= 0 && k >= 1, "sss_index_search_packed: bad nq / k");
   int64_t* I = (int64_t*)packed;
   float* D = (float*)((char*)packed + (size_t)nq * k * 8);
-  return search_all(ix, q, nq, k, mode, q_on_device, D, I, 1, stream, "sss_index_search_packed");
+  int* status = (int*)((char*)packed + sss_packed_bytes(nq, k) - 16);
+  {
+    DeviceGuard g(ix ? ix->device : 0);
+    SSS_CUDA_OK(cudaMemsetAsync(status, 0, 16, (cudaStream_t)stream));
+  }
+  return search_all(ix, q, nq, k, mode, q_on_device, D, I, 1, stream, "sss_index_search_packed", async ? status : nullptr);
 }
 
 extern "C" int sss_normalize(const float* in, float* out, int64_t n, int d, int norm_mode, int on_device, int device,
@@ -912,7 +925,7 @@ extern "C" int sss_topk_merge(const float* cand_D, const int64_t* cand_I, int n_
 }
 
 extern "C" int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k, int metric, float* D,
-                                     int64_t* I, int device, void* stream) {
+                                     int64_t* I, int* status_out, int device, void* stream) {
   SSS_REQUIRE(gathered && D && I, "sss_topk_merge_packed: NULL buffer");
   SSS_REQUIRE(n_shards >= 1 && k >= 1 && nq >= 0, "sss_topk_merge_packed: bad shape");
   DeviceGuard g(device);
@@ -920,7 +933,9 @@ extern "C" int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t
   const int64_t block = sss_packed_bytes(nq, k);
   const int64_t* cI = (const int64_t*)gathered;
   const float* cD = (const float*)((const char*)gathered + (size_t)nq * k * 8);
-  return launch_topk_merge(cD, cI, block / 4, block / 8, n_shards, nq, k, metric, D, I, (cudaStream_t)stream);
+  const int* st_in = (const int*)((const char*)gathered + block - 16);
+  return launch_topk_merge(cD, cI, block / 4, block / 8, n_shards, nq, k, metric, D, I, (cudaStream_t)stream, st_in,
+                           block / 4, status_out);
 }
 
 // ---------------------------------------------------------------------------------------------------

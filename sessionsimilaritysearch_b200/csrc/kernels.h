@@ -137,11 +137,13 @@ struct RefineArgs {
 };
 // group by session, (EXACT) prune + re-score survivors, keep the best k, raise the threshold
 int launch_refine(const RefineArgs& a, SelectState st, int num_sms, cudaStream_t stream);
-int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
+int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I, int* status_out,
                 cudaStream_t stream);
 // shard s: scores at cD + s * stride_d, ids at cI + s * stride_i (element strides)
+// status_in (optional): one status word per shard, status_stride ints apart; their OR is written to status_out
 int launch_topk_merge(const float* cD, const int64_t* cI, int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
-                      int k, int metric, float* D, int64_t* I, cudaStream_t stream);
+                      int k, int metric, float* D, int64_t* I, cudaStream_t stream, const int* status_in = nullptr,
+                      int64_t status_stride = 0, int* status_out = nullptr);
 // addresses of the two kernels whose pointer arguments a captured search graph re-binds per call (api.cu)
 const void* emit_kernel_addr();
 const void* prep_queries_kernel_addr();

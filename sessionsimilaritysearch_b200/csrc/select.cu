@@ -712,9 +712,15 @@ int launch_bootstrap_thr(const float* cmax, int n_chunks, int64_t nq, int64_t nq
 }
 
 // ---- emit -------------------------------------------------------------------------------------------
+// status_out (optional): the search's status word (overflow bits | watchdog code << 8) is OR-ed into it, so that an
+// asynchronous caller (the sharded path) can carry it inside the packed candidate block instead of stopping to read it
 __global__ void emit_kernel(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* __restrict__ D,
-                            int64_t* __restrict__ I) {
+                            int64_t* __restrict__ I, int* __restrict__ status_out) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 && status_out != nullptr) {
+    const int v = st.overflow[0] | (st.overflow[1] << 8);
+    if (v != 0) atomicOr(status_out, v);
+  }
   if (t >= nq * k) return;
   int64_t q = t / k;
   int j = (int)(t % k);
@@ -729,11 +735,11 @@ __global__ void emit_kernel(SelectState st, int64_t nq, int k, int metric, int64
   }
 }
 
-int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I,
+int launch_emit(SelectState st, int64_t nq, int k, int metric, int64_t id_offset, float* D, int64_t* I, int* status_out,
                 cudaStream_t stream) {
   int64_t total = nq * k;
   if (total <= 0) return 0;
-  emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(st, nq, k, metric, id_offset, D, I);
+  emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(st, nq, k, metric, id_offset, D, I, status_out);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -747,8 +753,14 @@ const void* emit_kernel_addr() { return (const void*)emit_kernel; }
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cD, const int64_t* __restrict__ cI,
                                                          int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
                                                          int k, int metric, int P, float* __restrict__ D,
-                                                         int64_t* __restrict__ I) {
+                                                         int64_t* __restrict__ I, const int* __restrict__ status_in,
+                                                         int64_t status_stride, int* __restrict__ status_out) {
   extern __shared__ uint64_t sm[];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && status_out != nullptr) {  // OR of the shards' status words
+    int v = 0;
+    for (int s = 0; s < n_shards; ++s) v |= status_in[(int64_t)s * status_stride];
+    *status_out = v;
+  }
   uint64_t* keys = sm;                 // [P] key in the high word (0 = empty)
   int64_t* ids = (int64_t*)(sm + P);   // [P]
   const int64_t q = blockIdx.x;
@@ -801,7 +813,8 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
 }
 
 int launch_topk_merge(const float* cD, const int64_t* cI, int64_t stride_d, int64_t stride_i, int n_shards, int64_t nq,
-                      int k, int metric, float* D, int64_t* I, cudaStream_t stream) {
+                      int k, int metric, float* D, int64_t* I, cudaStream_t stream, const int* status_in,
+                      int64_t status_stride, int* status_out) {
   if (nq <= 0 || k <= 0) return 0;
   int total = n_shards * k;
   int P = 2;
@@ -810,7 +823,8 @@ int launch_topk_merge(const float* cD, const int64_t* cI, int64_t stride_d, int6
   SSS_REQUIRE(smem <= 128 * 1024, "sss_topk_merge: n_shards * k must be <= 8192");
   static SmemAttr attr;
   if (attr.ensure(topk_merge_kernel, (int)smem)) return 1;
-  topk_merge_kernel<<<(unsigned)nq, 256, smem, stream>>>(cD, cI, stride_d, stride_i, n_shards, nq, k, metric, P, D, I);
+  topk_merge_kernel<<<(unsigned)nq, 256, smem, stream>>>(cD, cI, stride_d, stride_i, n_shards, nq, k, metric, P, D, I,
+                                                         status_in, status_stride, status_out);
   SSS_CUDA_OK(cudaGetLastError());
   return 0;
 }

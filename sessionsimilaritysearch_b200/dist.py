@@ -42,24 +42,31 @@ def cuda_merge(cand_D, cand_I, metric=_lib.METRIC_IP):
     return D, I
 
 
-def cuda_merge_packed(gathered, n_shards, nq, k, metric=_lib.METRIC_IP):
-    """sss_topk_merge_packed: `gathered` is the all-gathered uint8 tensor of n_shards packed candidate blocks"""
+def cuda_merge_packed(gathered, n_shards, nq, k, metric=_lib.METRIC_IP, out=None):
+    """sss_topk_merge_packed: `gathered` is the all-gathered uint8 tensor of n_shards packed candidate blocks.
+    Returns (D, I, status): status is a device int32 [1], the OR of the shards' status words."""
     import torch
     lib = _lib.load()
     dev = gathered.device.index
-    D = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
-    I = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
-    _lib.check(lib.sss_topk_merge_packed(gathered.data_ptr(), n_shards, nq, k, metric, D.data_ptr(), I.data_ptr(), dev,
-                                         _lib.current_stream(dev)))
-    return D, I
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.float32, device=gathered.device),
+               torch.empty((nq, k), dtype=torch.int64, device=gathered.device),
+               torch.empty(1, dtype=torch.int32, device=gathered.device))
+    D, I, status = out
+    _lib.check(lib.sss_topk_merge_packed(gathered.data_ptr(), n_shards, nq, k, metric, D.data_ptr(), I.data_ptr(),
+                                         status.data_ptr(), dev, _lib.current_stream(dev)))
+    return D, I, status
+
+
+def packed_bytes(nq, k):
+    return (nq * k * 12 + 15) // 16 * 16 + 16
 
 
 def pack_candidates(D, I):
     """host-side restatement of the packed block layout (CPU tests of the sharded logic): uint8 [packed_bytes]"""
     import torch
     nq, k = D.shape
-    n = (nq * k * 12 + 15) // 16 * 16
-    out = torch.zeros(n, dtype=torch.uint8)
+    out = torch.zeros(packed_bytes(nq, k), dtype=torch.uint8)
     out[:nq * k * 8] = I.contiguous().view(-1).view(torch.uint8)
     out[nq * k * 8:nq * k * 12] = D.contiguous().view(-1).view(torch.uint8)
     return out
@@ -68,8 +75,7 @@ def pack_candidates(D, I):
 def unpack_candidates(gathered, n_shards, nq, k):
     """inverse of the packed layout for n_shards blocks laid end to end -> (D [ns, nq, k], I [ns, nq, k])"""
     import torch
-    blk = (nq * k * 12 + 15) // 16 * 16
-    g = gathered.view(n_shards, blk)
+    g = gathered.view(n_shards, packed_bytes(nq, k))
     I = g[:, :nq * k * 8].contiguous().view(torch.int64).view(n_shards, nq, k)
     D = g[:, nq * k * 8:nq * k * 12].contiguous().view(torch.float32).view(n_shards, nq, k)
     return D, I
@@ -92,6 +98,7 @@ class ShardedIndex:
         self.merge_fn = merge_fn
         self.metric = metric
         self._gathered = None
+        self._mine = None
 
     @property
     def ntotal(self):
@@ -122,12 +129,28 @@ class ShardedIndex:
             if host_in and type(Dm).__module__.startswith("torch"):
                 return Dm.numpy(), Im.numpy()
             return Dm, Im
-        mine = self.inner.search_packed(x, k, **kw)
+        # asynchronous pipeline: shard search (captured graph) -> ONE all-gather -> merge, all enqueued back to back;
+        # the only host round trip is the status word at the very end
         nq = x.shape[0]
-        if self._gathered is None or self._gathered.numel() != self.world_size * mine.numel():
-            self._gathered = torch.empty(self.world_size * mine.numel(), dtype=torch.uint8, device=mine.device)
-        dist.all_gather_into_tensor(self._gathered, mine, group=self.group)  # rank-major concatenation
-        Dm, Im = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
+        n = packed_bytes(nq, k)
+        if self._mine is None or self._mine.numel() != n:
+            import torch as _t
+            dev = _t.device("cuda", self.inner.device)
+            self._mine = _t.empty(n, dtype=_t.uint8, device=dev)
+            self._gathered = _t.empty(self.world_size * n, dtype=_t.uint8, device=dev)
+        self.inner.search_packed(x, k, out=self._mine, asynchronous=True, **kw)
+        dist.all_gather_into_tensor(self._gathered, self._mine, group=self.group)  # rank-major concatenation
+        Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
         if host_in:
-            return Dm.cpu().numpy(), Im.cpu().numpy()
+            Dh, Ih = Dm.cpu(), Im.cpu()   # (synchronises: the status word is final by then)
+        if int(status.item()) != 0:
+            # some shard overflowed its candidate lists (every rank sees the same OR-ed word): repeat with the
+            # synchronous form, whose driver re-runs the shard search with a safer schedule
+            self.inner.search_packed(x, k, out=self._mine, asynchronous=False, **kw)
+            dist.all_gather_into_tensor(self._gathered, self._mine, group=self.group)
+            Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
+            if host_in:
+                Dh, Ih = Dm.cpu(), Im.cpu()
+        if host_in:
+            return Dh.numpy(), Ih.numpy()
         return Dm, Im

@@ -106,9 +106,11 @@ class _FlatIndex:
                                          _lib.current_stream(self.device)))
         return D, I
 
-    def search_packed(self, x, k, mode=None):
+    def search_packed(self, x, k, mode=None, out=None, asynchronous=False):
         """The sharded path's form of search(): one uint8 CUDA tensor holding this shard's candidates as
-        [ids int64 nq*k | scores fp32 nq*k] (sss_packed_bytes), ready to be all-gathered as it is."""
+        [ids int64 nq*k | scores fp32 nq*k | pad | 16-byte status trailer] (sss_packed_bytes), ready to be all-gathered
+        as it is.  asynchronous=True returns as soon as the work is enqueued: the status word (overflow -> the search
+        must be repeated synchronously) travels in the trailer and is checked by the caller after the merge."""
         import torch
         m = MODES[self.mode if mode is None else mode]
         k = int(k)
@@ -119,8 +121,10 @@ class _FlatIndex:
         else:
             x = _f32_host(x, self.d)
             ptr, on_dev, nq = x.ctypes.data, 0, x.shape[0]
-        out = torch.empty(int(self._lib.sss_packed_bytes(nq, k)), dtype=torch.uint8, device=dev)
-        check(self._lib.sss_index_search_packed(self._h, ptr, nq, k, m, on_dev, out.data_ptr(),
+        n = int(self._lib.sss_packed_bytes(nq, k))
+        if out is None or out.numel() != n:
+            out = torch.empty(n, dtype=torch.uint8, device=dev)
+        check(self._lib.sss_index_search_packed(self._h, ptr, nq, k, m, on_dev, out.data_ptr(), int(bool(asynchronous)),
                                                 _lib.current_stream(self.device)))
         return out
 

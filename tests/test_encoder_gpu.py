@@ -246,3 +246,69 @@ def test_end_to_end_sessions_to_topk(oracle):
     Dh, Ih = bi.search(qcodes, 20)
     Dho, Iho = oracle.search_hamming(dcodes.cpu().numpy(), qcodes.cpu().numpy(), 20)
     assert np.array_equal(Dh.cpu().numpy(), Dho) and np.array_equal(Ih.cpu().numpy(), Iho)
+
+
+def test_config0_ten_thousand_sessions_eval_against_the_oracle_chain():
+    """BASELINE configs[0] at its stated size (test_amazon_filterd.py:485-578 on ~10k sessions): database =
+    encode(prefix + suffix) of 10,000 synthetic Amazon-filtered-shaped sessions, queries = encode(prefix) of 2,000 of
+    them, reference model shape (768 -> 3 x 800 -> 3168 -> 1600), batches of 200, cosine top-100.  The CUDA chain
+    (native featuriser -> fused tcgen05 encoder -> tensor-core search) against the CPU oracle chain (encoder oracle ->
+    fixed-order search oracle): embeddings inside 3e-4 of the output scale, recall@100 >= 0.999, scores inside 1e-3; and
+    on identical embeddings the search is bit-exact."""
+    import sessionsimilaritysearch_b200 as sss
+    from oracle import encoder_oracle as eo
+    from oracle import search_oracle as so
+    from sessionsimilaritysearch_b200 import featurize, graph, pipeline, sessions, synth
+    in_dim, hidden, n_layers, out_dim, msl = 768, 800, 3, 1600, 20
+    n_db, n_q = 10000, 2000
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 31)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    rng = np.random.default_rng(32)
+    full = synth.make_sessions(n_db, 33)
+    pairs = [synth.split_session(s, rng) for s in full]
+    queries = [p for p, _ in pairs[:n_q]]
+    vocab = featurize.QueryVocab()
+    items = {0}
+    for s in full:
+        for act in s:
+            if act[1] == sessions.SEARCH:
+                vocab(act[2])
+            else:
+                items.add(act[-1])
+    item_ids = np.asarray(sorted(items), dtype=np.int64)
+    g = torch.Generator().manual_seed(34)
+    qf, itf = torch.randn((len(vocab), in_dim), generator=g), torch.randn((len(item_ids), in_dim), generator=g)
+    cache = featurize.FeatureCache(qf, item_ids, itf, 0)
+    db_gpu, _ = pipeline.encode_sessions(enc, featurize.flatten(full, vocab), cache)
+    q_gpu, _ = pipeline.encode_sessions(enc, featurize.flatten(queries, vocab), cache)
+    # the oracle chain on the same batches (a batch of 200 is its own graph batch: GATConv's self-loop quirk)
+    host_cache = featurize.FeatureCache(qf, item_ids, itf, "cpu")
+
+    def oracle_encode(sess_list):
+        flat = featurize.flatten(sess_list, vocab)
+        out = []
+        for lo in range(0, len(flat), 200):
+            b = featurize.featurize_batch(flat.slice(lo, min(len(flat), lo + 200)), host_cache)
+            out.append(eo.encoder_forward(P, eo.batch_from_pyg(b), n_layers))
+        return torch.cat(out).numpy()
+
+    db_cpu = oracle_encode(full[:2000])           # the encoder oracle on a 2,000-session slice (time)
+    scale = float(np.abs(db_cpu).max())
+    np.testing.assert_allclose(db_gpu[:2000].cpu().numpy(), db_cpu, rtol=3e-4, atol=3e-4 * scale)
+    index = sss.build_index(db_gpu, 'cos')
+    D, I = index.search(sss.normalize(q_gpu), 100)
+    D, I = D.cpu().numpy(), I.cpu().numpy()
+    # search parity on the very same embeddings: ids and scores bit for bit
+    Do, Io = so.search_flat(so.normalize(db_gpu.cpu().numpy(), 1), so.normalize(q_gpu.cpu().numpy(), 1)[:64], 100)
+    assert np.array_equal(I[:64], Io) and np.array_equal(D[:64].view(np.uint32), Do.view(np.uint32))
+    # the query prefix must find its own session
+    assert float((I[:, 0] == np.arange(n_q)).mean()) >= 0.4   # (random-init weights, uniformly random split point)
+    # whole-chain agreement where both chains were run: oracle embeddings of the first 2,000 database sessions
+    q_cpu = oracle_encode(queries[:200])
+    sub = sss.build_index(db_gpu[:2000].contiguous(), 'cos')
+    Ds, Is = sub.search(sss.normalize(q_gpu[:200].contiguous()), 100)
+    Dc, Ic = so.search_flat(so.normalize(db_cpu, 1), so.normalize(q_cpu, 1), 100)
+    Is, Ds = Is.cpu().numpy(), Ds.cpu().numpy()
+    recall = np.mean([len(set(Is[r]) & set(Ic[r])) / 100.0 for r in range(200)])
+    assert recall >= 0.999, recall
+    assert np.max(np.abs(Ds - Dc)) < 1e-3
