@@ -778,7 +778,9 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
     if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, b.status_out, safe, ix->profile, st)) return 1;
     ix->stat_kernels += c.kernels;
     ix->stat_waves += c.waves;
-    if (b.status_out != nullptr) return 0;  // asynchronous form: the caller reads the status word when it suits it
+    // asynchronous form: the caller reads the status word when it suits it (a profiled search stays synchronous: its
+    // CUDA events are read below)
+    if (b.status_out != nullptr && !ix->profile) return 0;
     SSS_CUDA_OK(cudaMemcpyAsync(ws.host_flags, ws.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!b.out_on_device) {
       SSS_CUDA_OK(cudaMemcpyAsync(b.D, Ddev, (size_t)b.nq * b.k * sizeof(float), cudaMemcpyDeviceToHost, st));
