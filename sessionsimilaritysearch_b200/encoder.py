@@ -37,6 +37,8 @@ class SessionEncoder:
         h = ctypes.c_void_p()
         check(self._lib.sss_encoder_create(ctypes.byref(h), self.device, ctypes.byref(shape)))
         self._h = h
+        self._pending = []
+        self._keep = None
         self.load_state_dict(params)
         # dense linears: this library's split-bf16 tcgen05 GEMM (2.7e-5 of the output scale from float64), the only
         # arithmetic of the C ABI
@@ -104,22 +106,36 @@ class SessionEncoder:
                             pp.shape[1], rows[4].data_ptr(), rows[5].data_ptr())
         return b, keep, n_graphs
 
-    def _run(self, b, out=None, zq=None, zp=None, run_gnn=True, run_pooling=True):
+    def _run(self, b, out=None, zq=None, zp=None, run_gnn=True, run_pooling=True, defer_check=False):
         dev = torch.device("cuda", self.device)
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         io = _lib.EncoderIO(out.data_ptr() if out is not None else None, zq.data_ptr() if zq is not None else None,
                             zp.data_ptr() if zp is not None else None, int(run_gnn), int(run_pooling), flag.data_ptr())
         check(self._lib.sss_encoder_forward_ex(self._h, ctypes.byref(b), ctypes.byref(io),
                                                _lib.current_stream(self.device)))
+        if defer_check:                       # the caller collects the flags and checks them once (check_flags)
+            self._pending.append(flag)
+            return
         if int(flag.item()) != 0:             # the reference's isnan asserts (model/model.py:301-314)
             raise RuntimeError("nan in embedding[query]")
+
+    def check_flags(self):
+        """the NaN checks of every forward run with defer_check=True since the last call, in ONE device read-back"""
+        if self._pending:
+            bad = int(torch.stack(self._pending).sum().item())
+            self._pending = []
+            if bad != 0:
+                raise RuntimeError("nan in embedding[query]")
 
     @property
     def node_dim(self):
         return self.in_dim + self.n_layers * self.hidden
 
-    def __call__(self, data, query_node_mask=None, product_node_mask=None, get_node=False, get_token=False):
-        """encoder(data, ...) of model/model.py:279-351.  get_node=True also returns the node embeddings
+    def __call__(self, data, query_node_mask=None, product_node_mask=None, get_node=False, get_token=False,
+                 defer_check=False):
+        """encoder(data, ...) of model/model.py:279-351.  defer_check=True skips the per-call device read-back of the
+        NaN flag (the reference's three isnan asserts cost it three host syncs per batch); call check_flags() after a
+        run of batches instead — the host can then prepare batch i + 1 while the GPU encodes batch i.  get_node=True also returns the node embeddings
         {'query': [N_q, 3168], 'product': [N_p, 3168]}; get_token=True returns the reference's (empty)
         session_level_token_emb dict — the block that would fill it is commented out there (model/model.py:321-332)."""
         dev = torch.device("cuda", self.device)
@@ -135,7 +151,8 @@ class SessionEncoder:
         if get_node:
             zq = torch.empty((xq.shape[0], self.node_dim), dtype=torch.float32, device=dev)
             zp = torch.empty((xp.shape[0], self.node_dim), dtype=torch.float32, device=dev)
-        self._run(b, out, zq, zp)
+        self._run(b, out, zq, zp, defer_check=defer_check)
+        self._keep = keep if defer_check else None   # (inputs of an unsynchronised forward must outlive the call)
         del keep
         if not get_node and not get_token:
             return out

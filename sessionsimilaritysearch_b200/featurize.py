@@ -129,9 +129,26 @@ def featurize_batch(flat, cache, root_query_key=0, n_threads=0):
     graph.collate([sequence_to_graph(...), ...]) with the text features already in place)."""
     a = featurize_arrays(flat, root_query_key, n_threads)
     dev = cache.device
+    # ONE host -> device copy per dtype for the whole batch (a dozen small pageable copies cost more than the native
+    # featuriser itself): the arrays are laid end to end and sliced on the device
+    i_keys = ("query_key", "query_pos", "query_batch", "product_key", "product_cnt", "product_batch", "product_pos",
+              "qp_src", "qp_dst", "pp_src", "pp_dst")
+    a["item_rows"] = cache.item_rows(a["product_key"]).astype(np.int64, copy=False)
+    i_keys = i_keys + ("item_rows",)
+    f_keys = ("pp_weight", "last_click_mask")
+    i_all = torch.from_numpy(np.concatenate([a[k] for k in i_keys])).to(dev, non_blocking=True)
+    f_all = torch.from_numpy(np.concatenate([a[k] for k in f_keys])).to(dev, non_blocking=True)
+    dv, off = {}, 0
+    for k in i_keys:
+        dv[k] = i_all[off:off + len(a[k])]
+        off += len(a[k])
+    off = 0
+    for k in f_keys:
+        dv[k] = f_all[off:off + len(a[k])]
+        off += len(a[k])
 
     def t(x):
-        return torch.from_numpy(x).to(dev, non_blocking=True)
+        return x
 
     def rows(table, idx):  # feature gather: the library's kernel on the device, plain indexing for a host cache
         if table.device.type == "cuda":
@@ -142,22 +159,22 @@ def featurize_batch(flat, cache, root_query_key=0, n_threads=0):
     out = SessionBatch()
     out.num_graphs = a["n_graphs"]
     q = out["query"]
-    q.x = rows(cache.query_features, t(a["query_key"]))
-    q.pos_emb_id = t(a["query_pos"])
-    q.batch = t(a["query_batch"])
+    q.x = rows(cache.query_features, dv["query_key"])
+    q.pos_emb_id = dv["query_pos"]
+    q.batch = dv["query_batch"]
     q.num_nodes = len(a["query_key"])
     p = out["product"]
-    p.x = t(a["product_key"])
-    p.input_ids = rows(cache.item_features, t(cache.item_rows(a["product_key"])))
-    p.cnt = t(a["product_cnt"])
-    p.pos_emb_id = t(a["product_pos"])
-    p.batch = t(a["product_batch"])
-    p.last_click_mask = t(a["last_click_mask"])
+    p.x = dv["product_key"]
+    p.input_ids = rows(cache.item_features, dv["item_rows"])
+    p.cnt = dv["product_cnt"]
+    p.pos_emb_id = dv["product_pos"]
+    p.batch = dv["product_batch"]
+    p.last_click_mask = dv["last_click_mask"]
     p.num_nodes = len(a["product_key"])
-    qp = torch.stack([t(a["qp_src"]), t(a["qp_dst"])])
+    qp = torch.stack([dv["qp_src"], dv["qp_dst"]])
     out[EDGE_QP].edge_index = qp
     out[EDGE_PQ].edge_index = qp.flip(0)
     pp = out[EDGE_PP]
-    pp.edge_index = torch.stack([t(a["pp_src"]), t(a["pp_dst"])])
-    pp.edge_weight = t(a["pp_weight"])
+    pp.edge_index = torch.stack([dv["pp_src"], dv["pp_dst"]])
+    pp.edge_weight = dv["pp_weight"]
     return out

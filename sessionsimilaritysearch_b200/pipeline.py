@@ -30,7 +30,8 @@ def encode_sessions(enc, flat, cache, batch=200):
         t0 = time.perf_counter()
         b = featurize.featurize_batch(flat.slice(lo, hi), cache)
         t_feat += time.perf_counter() - t0
-        out[lo:hi] = enc(b)
+        out[lo:hi] = enc(b, defer_check=True)   # no host sync per batch: the next batch is featurised meanwhile
+    enc.check_flags()
     return out, t_feat
 
 
