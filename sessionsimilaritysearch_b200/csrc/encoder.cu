@@ -23,6 +23,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -423,6 +424,7 @@ struct sss_encoder {
   cudaEvent_t done = nullptr;
   bool done_recorded = false;
   int64_t launches = 0;   // kernels of the last forward
+  int64_t host_ns = 0;    // host time the last forward spent enqueueing them
 };
 
 namespace {
@@ -643,7 +645,7 @@ extern "C" int sss_encoder_set_math(sss_encoder_t* e, int math) {
 extern "C" int sss_encoder_get_math(const sss_encoder_t* e) { return e ? SSS_ENCODER_MATH_BF16X3 : -1; }
 extern "C" int64_t sss_encoder_stat(const sss_encoder_t* e, int what) {
   if (!e) return -1;
-  return what == 0 ? e->launches : -1;
+  return what == 0 ? e->launches : what == 1 ? e->host_ns : -1;
 }
 
 extern "C" int sss_encoder_destroy(sss_encoder_t* e) {
@@ -726,6 +728,12 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
   } restore{prev};
   cudaStream_t st = (cudaStream_t)stream;
   if (prepare_weights(e, st)) return 1;
+  const auto t_host0 = std::chrono::steady_clock::now();
+  struct HostClock {
+    sss_encoder* e;
+    std::chrono::steady_clock::time_point t0;
+    ~HostClock() { e->host_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+  } host_clock{e, t_host0};
   if (ws_begin(e, st)) return 1;
   e->launches = 0;
 
@@ -748,11 +756,11 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
       ws_alloc(e, &zp_hi, (size_t)NPp * ZDp) || ws_alloc(e, &zp_lo, (size_t)NPp * ZDp) ||
       ws_alloc(e, &u_hi, (size_t)NTp * OUTp) || ws_alloc(e, &u_lo, (size_t)NTp * OUTp) ||
       ws_alloc(e, &c_hi, (size_t)Bp * OUTp) || ws_alloc(e, &c_lo, (size_t)Bp * OUTp) ||
-      ws_alloc(e, &Sq, (size_t)NQ * LDQ) || ws_alloc(e, &Sp, (size_t)NP * LDP) || ws_alloc(e, &asq, (size_t)NQ * T) ||
-      ws_alloc(e, &adq, (size_t)NQ * T) || ws_alloc(e, &adp, (size_t)NP * T) || ws_alloc(e, &asp, (size_t)NP * T) ||
+      ws_alloc(e, &Sq, (size_t)NQ * LDQ) || ws_alloc(e, &Sp, (size_t)NP * LDP) || ws_alloc(e, &asq, (size_t)NQ * T * 2) ||
+      ws_alloc(e, &adq, (size_t)NQ * T * 2) || ws_alloc(e, &adp, (size_t)NP * T * 2) || ws_alloc(e, &asp, (size_t)NP * T * 2) ||
       ws_alloc(e, &Gp, (size_t)NP * H) || ws_alloc(e, &agg_hi, (size_t)NPp * Hp) || ws_alloc(e, &agg_lo, (size_t)NPp * Hp) ||
       ws_alloc(e, &U, (size_t)NT * OUT) || ws_alloc(e, &Bc, (size_t)B * OUT) ||
-      ws_alloc(e, &att_part, (size_t)NT * tiles_out) || ws_alloc(e, &prefix, NP + 1) || ws_alloc(e, &node_graph, NT + 1) ||
+      ws_alloc(e, &att_part, (size_t)NT * tiles_out * 2) || ws_alloc(e, &prefix, NP + 1) || ws_alloc(e, &node_graph, NT + 1) ||
       ws_alloc(e, &ranges, (size_t)B * 4) || ws_alloc(e, &cnt_i, NP + 1))
     return 1;
   for (int j = 0; j < 3; ++j)
@@ -829,7 +837,7 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
     g2[1].att_width = H;
     if (launch_gemm_bf16x3(g2, 2, e->gemm_flag, st)) return 1;
     MpArgs ma{};
-    ma.n_p = NP; ma.n_q = NQ; ma.H = H; ma.parts = T;
+    ma.n_p = NP; ma.n_q = NQ; ma.H = H; ma.parts = 2 * T;   // (row, 128-column sub-tile, epilogue warpgroup)
     ma.qp_rowptr = rowptr[0]; ma.qp_col = col[0]; ma.pq_rowptr = rowptr[1]; ma.pq_col = col[1];
     ma.pp_rowptr = rowptr[2]; ma.pp_col = col[2];
     ma.Sq = Sq; ma.ldsq = LDQ; ma.Sp = Sp; ma.ldsp = LDP; ma.PP = PP;
@@ -902,7 +910,7 @@ extern "C" int sss_encoder_forward_ex(sss_encoder_t* e, const sss_graph_batch_t*
   gn.ap_w = wa;
   gn.ap_out = att_part;
   if (launch_gemm_bf16x3(&gn, 1, e->gemm_flag, st)) return 1;
-  graph_weighted_mean_kernel<<<dim3(B, col_blocks), 256, 1024 * sizeof(float), st>>>(U, OUT, ranges, att_part, tiles_out, out);
+  graph_weighted_mean_kernel<<<dim3(B, col_blocks), 256, 1024 * sizeof(float), st>>>(U, OUT, ranges, att_part, 2 * tiles_out, out);
   e->launches += 5;
   SSS_CUDA_OK(cudaGetLastError());
   return ws_end(e, st);

@@ -49,12 +49,12 @@ namespace sss {
 
 namespace {
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;             // 4 role warps + 2 epilogue warpgroups
 constexpr int kGemmStageBytes = 4 * kKBlockBytes;  // Ah | Al | Bh | Bl
 constexpr int kGemmStages = 3;
 constexpr uint32_t kGemmTmemCols = 256;            // two accumulators of 128 columns
-constexpr int kGemmXposePitch = 33;
-constexpr int kGemmXposeBytes = 128 * kGemmXposePitch * 4;
+constexpr int kGemmXposePitch = 17;
+constexpr int kGemmXposeBytes = 2 * 128 * kGemmXposePitch * 4;  // one [128][17] transpose buffer per epilogue warpgroup
 constexpr int kGemmSmemBytes = 1024 + kGemmStages * kGemmStageBytes + kGemmXposeBytes + 256;
 
 struct GemmLaunch {
@@ -89,7 +89,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
   const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * xc));
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+// the 4 warps of epilogue warpgroup wg (named barriers 1 and 2)
+__device__ __forceinline__ void epi_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
 struct TileRef {
   int which, tile_m, tile_n, m0, n0;
@@ -149,7 +150,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * s, 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -233,11 +234,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps): TMEM -> registers -> [128][33] transpose -> coalesced global ==========
+    // ===================== epilogue (8 warps = 2 warpgroups) =====================
+    // Both warpgroups read every 32-column chunk of the accumulator, 16 columns each (a warp may only touch the TMEM
+    // lanes of its quarter, so the tile is split by columns, not rows): TMEM -> registers (a thread owns one output
+    // row; row-wise reductions finish here) -> [128][17] shared-memory transpose -> phase 2, where 16 consecutive
+    // threads touch 16 consecutive columns of one row of global memory.
+    const int ew = warp - 4;
+    const int wg = ew >> 2;
     const int quarter = warp & 3;
-    const int rl = quarter * 32 + lane;      // phase 1: this thread's row inside the tile
-    const int e = (int)threadIdx.x - 128;    // phase 2: lane = column inside the chunk, e >> 5 = row group
-    const int pc = e & 31, pr = e >> 5;
+    const int rl = quarter * 32 + lane;                  // phase 1: this thread's row inside the tile
+    const int e = (int)threadIdx.x - 128 - wg * 128;     // phase 2: e & 15 = column inside the half chunk, e >> 4 = row group
+    const int pc = e & 15, pr = e >> 4;
+    const int hc = 16 * wg;                              // this warpgroup's columns inside a chunk
+    float* const xp = xpose + wg * (kTileQ * kGemmXposePitch);
     uint32_t it = 0;
     for (int t = pair; t < L.tiles_total; t += n_pairs, ++it) {
       const TileRef tr = tile_of(L, t);
@@ -249,15 +258,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
       const int rows_valid = min(kTileQ, g.M - m0);
       mbar_wait(tfull_bar + 8 * slot, (it >> 1) & 1u, L.err_flag, 505);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u + (uint32_t)hc;
       const int n_chunks = g.bn / 32;
       float partial = 0.0f;
       const float* bc = (g.epi == EPI_ATTPOOL && row_ok) ? g.ap_bc + (size_t)g.ap_node_graph[row] * (size_t)g.N : nullptr;
-      float rg[32], zg[32];  // EPI_GRU: gates of this thread's phase-2 elements (row group k, unit pc)
+      float rg[16], zg[16];  // EPI_GRU: gates of this thread's phase-2 elements (row group k, unit pc)
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), r);
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
         if (c + 1 == n_chunks) {  // the accumulator has left TMEM: hand the slot back to the MMA warp
           tc_fence_before();
@@ -266,9 +275,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
         }
         if (g.epi == EPI_ATTPOOL) {
           if (row_ok) {
-            const int col0 = n0 + c * 32;
+            const int col0 = n0 + c * 32 + hc;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const int col = col0 + i;
               if (col < g.N) partial += g.ap_w[col] * fast_sigmoid(__uint_as_float(r[i]) + g.bias[col] + bc[col]);
             }
@@ -276,33 +285,34 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
           continue;
         }
         if (g.epi == EPI_ATT) {
-          // attention logits: one partial per (row, 128-column sub-tile); a sub-tile lies inside one part
+          // attention logits: one partial per (row, 128-column sub-tile, warpgroup); a sub-tile lies inside one part
           const int sub = (n0 + c * 32) / 128;                 // 128-column sub-tile of the whole output
           const int part = sub / g.att_tiles_per_part;
           const float* att = part < 4 ? g.att[part] : nullptr;
           if (att != nullptr) {
-            const int pc0 = (sub - part * g.att_tiles_per_part) * 128 + (c & 3) * 32;  // column inside the part
+            const int pc0 = (sub - part * g.att_tiles_per_part) * 128 + (c & 3) * 32 + hc;  // column inside the part
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < 16; ++i)
               if (pc0 + i < g.att_width) partial = fmaf(__uint_as_float(r[i]), att[pc0 + i], partial);
             if ((c & 3) == 3) {
-              if (row_ok) g.att_out[part][(size_t)row * g.att_tiles_per_part + (sub - part * g.att_tiles_per_part)] = partial;
+              if (row_ok)
+                g.att_out[part][((size_t)row * g.att_tiles_per_part + (sub - part * g.att_tiles_per_part)) * 2 + wg] = partial;
               partial = 0.0f;
             }
           }
         }
-        epi_bar();  // the previous chunk's readers are done with the transpose buffer
+        epi_bar(wg);  // the previous chunk's readers are done with the transpose buffer
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xpose[rl * kGemmXposePitch + i] = __uint_as_float(r[i]);
-        epi_bar();
-        // ---- phase 2: element (row group k -> row 4k + pr, column pc of this chunk)
+        for (int i = 0; i < 16; ++i) xp[rl * kGemmXposePitch + i] = __uint_as_float(r[i]);
+        epi_bar(wg);
+        // ---- phase 2: element (row group k -> row 8k + pr, column pc of this half chunk)
         if (g.epi == EPI_STORE || g.epi == EPI_ATT) {
-          const int col = n0 + c * 32 + pc;
+          const int col = n0 + c * 32 + hc + pc;
           if (col < g.N) {
             const float bias = g.bias ? g.bias[col] : 0.0f;
-            for (int k = 0; 4 * k + pr < rows_valid; ++k) {
-              const int rr = 4 * k + pr;
-              float v = xpose[rr * kGemmXposePitch + pc] + bias;
+            for (int k = 0; 8 * k + pr < rows_valid; ++k) {
+              const int rr = 8 * k + pr;
+              float v = xp[rr * kGemmXposePitch + pc] + bias;
               if (g.sign_out) {
                 const float sg = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);
                 const float th = tanhf(v);
@@ -312,65 +322,61 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
             }
           }
         } else if (g.epi == EPI_GRU) {
-          // every 96 columns = 32 hidden units x (r | z | n): chunk c -> unit group c / 3, gate c % 3; lane = unit
+          // every 96 columns = 32 hidden units x (r | z | n): chunk c -> unit group c / 3, gate c % 3
           const int H = g.gru_H;
           const int gate = c % 3;
-          const int u = (tile_n * (g.bn / 96) + c / 3) * 32 + pc;
+          const int u = (tile_n * (g.bn / 96) + c / 3) * 32 + hc + pc;
           if (u < H) {
             const float bi = g.gru_b_ih[gate * H + u], bh = g.gru_b_hh[gate * H + u];
-            // all global operands of the chunk are requested before the first one is used: 32 independent loads in
-            // flight per thread instead of 32 serialised L2 round trips (160 us per launch that way)
+            // all global operands of the chunk are requested before the first one is used: independent loads in
+            // flight instead of serialised L2 round trips (160 us per launch that way)
             const float* ghp = g.gru_gh + (size_t)(m0 + pr) * (size_t)g.gru_gh_ld + gate * H + u;
-            const size_t gh_step = 4 * (size_t)g.gru_gh_ld;
-            float ghv[32];
+            const size_t gh_step = 8 * (size_t)g.gru_gh_ld;
+            float ghv[16];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) ghv[k] = 4 * k + pr < rows_valid ? __ldg(ghp + k * gh_step) : 0.0f;
+            for (int k = 0; k < 16; ++k) ghv[k] = 8 * k + pr < rows_valid ? __ldg(ghp + k * gh_step) : 0.0f;
             if (gate < 2) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const float gi = xpose[(4 * k + pr) * kGemmXposePitch + pc] + bi;
+              for (int k = 0; k < 16; ++k) {
+                const float gi = xp[(8 * k + pr) * kGemmXposePitch + pc] + bi;
                 const float sgm = fast_sigmoid(gi + ghv[k] + bh);
                 if (gate == 0) rg[k] = sgm; else zg[k] = sgm;
               }
             } else {
+              float xv[16], gpv[16];
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                float xv[16], gpv[16];
+              for (int k = 0; k < 16; ++k) {
+                const int rr = 8 * k + pr;
+                const bool ok = rr < rows_valid;
+                xv[k] = (ok && u < g.gru_in_w) ? __ldg(g.gru_x + (size_t)(m0 + rr) * (size_t)g.gru_x_ld + u) : 0.0f;
+                gpv[k] = ok ? __ldg(g.gru_gp + (size_t)(m0 + rr) * (size_t)H + u) : 0.0f;
+              }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int rr = 4 * (16 * half + j) + pr;
-                  const bool ok = rr < rows_valid;
-                  xv[j] = (ok && u < g.gru_in_w) ? __ldg(g.gru_x + (size_t)(m0 + rr) * (size_t)g.gru_x_ld + u) : 0.0f;
-                  gpv[j] = ok ? __ldg(g.gru_gp + (size_t)(m0 + rr) * (size_t)H + u) : 0.0f;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int k = 16 * half + j;
-                  const int rr = 4 * k + pr;
-                  if (rr < rows_valid) {
-                    const float gi = xpose[rr * kGemmXposePitch + pc] + bi;
-                    const float ng = fast_tanh(gi + rg[k] * (ghv[k] + bh));
-                    const float h = (1.0f - zg[k]) * ng + zg[k] * xv[j];
-                    const float o = fmaxf(gpv[j] + h, 0.0f);  // HeteroConv sum of both branches, relu
-                    g.C[(size_t)(m0 + rr) * (size_t)g.ldc + u] = o;
-                    store_hilo(g.out_hi, g.out_lo, (size_t)(m0 + rr) * g.out_ld + g.out_k0 + u, o);
-                  }
+              for (int k = 0; k < 16; ++k) {
+                const int rr = 8 * k + pr;
+                if (rr < rows_valid) {
+                  const float gi = xp[rr * kGemmXposePitch + pc] + bi;
+                  const float ng = fast_tanh(gi + rg[k] * (ghv[k] + bh));
+                  const float h = (1.0f - zg[k]) * ng + zg[k] * xv[k];
+                  const float o = fmaxf(gpv[k] + h, 0.0f);  // HeteroConv sum of both branches, relu
+                  g.C[(size_t)(m0 + rr) * (size_t)g.ldc + u] = o;
+                  store_hilo(g.out_hi, g.out_lo, (size_t)(m0 + rr) * g.out_ld + g.out_k0 + u, o);
                 }
               }
             }
           }
         } else if (g.epi == EPI_POOL) {
           const int W = g.pool_lin_w + g.pool_msl;
-          const int col = n0 + c * 32 + pc;
+          const int col = n0 + c * 32 + hc + pc;
           if (col < W) {
             const bool is_lin = col < g.pool_lin_w;
             const float bias = is_lin ? g.bias[col] : 0.0f;
             // output rows of an input row: a query -> one row after the product occurrences; a product -> one per
             // occurrence (repeat_interleave by cnt).  Row ranges first (independent loads), then the stores.
-            int t0v[32], t1v[32];
+            int t0v[16], t1v[16];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int rr = 4 * k + pr;
+            for (int k = 0; k < 16; ++k) {
+              const int rr = 8 * k + pr;
               const int grow = m0 + rr;
               t0v[k] = 0;
               t1v[k] = 0;
@@ -385,9 +391,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
               }
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int rr = 4 * k + pr;
-              const float lin = is_lin ? fast_tanh(xpose[rr * kGemmXposePitch + pc] + bias) : 0.0f;
+            for (int k = 0; k < 16; ++k) {
+              const int rr = 8 * k + pr;
+              const float lin = is_lin ? fast_tanh(xp[rr * kGemmXposePitch + pc] + bias) : 0.0f;
               for (int tt = t0v[k]; tt < t1v[k]; ++tt) {
                 float x = lin;
                 if (!is_lin) {
@@ -401,7 +407,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_ah0, const __grid_cons
           }
         }
       }
-      if (row_ok && g.epi == EPI_ATTPOOL) g.ap_out[(size_t)row * g.tiles_n + tile_n] = partial;
+      if (row_ok && g.epi == EPI_ATTPOOL) g.ap_out[((size_t)row * g.tiles_n + tile_n) * 2 + wg] = partial;
     }
   }
 

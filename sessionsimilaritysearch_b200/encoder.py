@@ -80,6 +80,11 @@ class SessionEncoder:
         """kernels launched by the last forward"""
         return int(self._lib.sss_encoder_stat(self._h, 0))
 
+    @property
+    def host_ns(self):
+        """host nanoseconds the last forward spent enqueueing its kernels (inside the C call)"""
+        return int(self._lib.sss_encoder_stat(self._h, 1))
+
     def eval(self):
         return self
 
@@ -94,7 +99,10 @@ class SessionEncoder:
         qb, pb = _i64(data["query"].batch, dev), _i64(data["product"].batch, dev)
         qpos, ppos = _i64(data["query"].pos_emb_id, dev), _i64(data["product"].pos_emb_id, dev)
         cnt = _i64(data["product"].cnt, dev)
-        n_graphs = int(max(int(qb.max()), int(pb.max()))) + 1
+        n_graphs = getattr(data, "num_graphs", None)   # (PyG batches and SessionBatch both carry it: no device read)
+        if n_graphs is None:
+            n_graphs = int(max(int(qb.max()), int(pb.max()))) + 1
+        n_graphs = int(n_graphs)
         rows = [qp[0].contiguous(), qp[1].contiguous(), pq[0].contiguous(), pq[1].contiguous(), pp[0].contiguous(),
                 pp[1].contiguous()]
         keep = [xq, xp, qb, pb, qpos, ppos, cnt] + rows
