@@ -79,6 +79,37 @@ def flatten(sessions, vocab, ignore_query=False):
     return FlatSessions(act_off, kinds, keys, uniq_off, uniq)
 
 
+def flatten_prefixes(sessions, vocab):
+    """FlatSessions of EVERY PREFIX of every session, contiguous per session (the database rows of the session-max
+    search: decompose_data-style splitting), plus seg_off [n_sessions + 1] — equal to
+    flatten([s[:j] for s in sessions for j in 1..len(s)]) without materialising the prefix lists: the sessions are
+    flattened once, the actions of the prefixes are gathered with index arithmetic, and only the node order of the
+    distinct items (list(set(ids)) per prefix, the reference's order) is taken from Python sets."""
+    base = flatten(sessions, vocab)
+    n_act = np.diff(base.act_off)                              # actions per session
+    seg_off = np.concatenate([[0], np.cumsum(n_act)]).astype(np.int64)   # prefixes per session = its actions
+    n_pref = int(seg_off[-1])
+    pref_sess = np.repeat(np.arange(len(n_act), dtype=np.int64), n_act)
+    pref_len = np.arange(n_pref, dtype=np.int64) - seg_off[pref_sess] + 1          # 1 .. n per session
+    act_off = np.concatenate([[0], np.cumsum(pref_len)]).astype(np.int64)
+    elem_pref = np.repeat(np.arange(n_pref, dtype=np.int64), pref_len)
+    src = np.arange(int(act_off[-1]), dtype=np.int64) - act_off[elem_pref] + base.act_off[pref_sess[elem_pref]]
+    kinds, keys = base.act_is_search[src], base.act_key[src]
+    # distinct items per prefix: consecutive prefixes between two clicks share their set
+    uniq_off, uniq = [0], []
+    is_search, key = base.act_is_search.tolist(), base.act_key.tolist()
+    a_off = base.act_off.tolist()
+    for i in range(len(n_act)):
+        items, cur = [], []
+        for a in range(a_off[i], a_off[i + 1]):
+            if not is_search[a]:
+                items.append(key[a])
+                cur = list(set(items))
+            uniq.extend(cur)
+            uniq_off.append(len(uniq))
+    return FlatSessions(act_off, kinds, keys, uniq_off, uniq), seg_off
+
+
 def featurize_arrays(flat, root_query_key=0, n_threads=0):
     """native call: FlatSessions -> dict of numpy arrays (batch-global indices)"""
     lib = _lib.load()

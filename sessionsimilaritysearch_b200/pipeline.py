@@ -19,20 +19,33 @@ from .dist import ShardedIndex
 from .index import IndexFlatIP, NORM_UTIL, normalize
 
 
-def encode_sessions(enc, flat, cache, batch=200):
+def encode_sessions(enc, flat, cache, batch=200, prefetch=2):
     """FlatSessions -> [n, out_dim] embeddings on the encoder's device, batches of `batch` sessions (the reference's
-    DataLoader batch size, test_amazon_filterd.py:488).  Returns (embeddings, seconds spent in the host featuriser)."""
+    DataLoader batch size, test_amazon_filterd.py:488).  Returns (embeddings, seconds spent in the host featuriser).
+    A worker thread featurises up to `prefetch` batches ahead (the native call releases the GIL) while this thread
+    enqueues the encoder; nothing synchronises with the device until the NaN flags are read once at the end."""
+    from concurrent.futures import ThreadPoolExecutor
     dev = torch.device("cuda", enc.device)
     out = torch.empty((len(flat), enc.out_dim), dtype=torch.float32, device=dev)
-    t_feat = 0.0
-    for lo in range(0, len(flat), batch):
-        hi = min(len(flat), lo + batch)
+    t_feat = [0.0]
+    bounds = [(lo, min(len(flat), lo + batch)) for lo in range(0, len(flat), batch)]
+
+    def make(lo, hi):
         t0 = time.perf_counter()
-        b = featurize.featurize_batch(flat.slice(lo, hi), cache)
-        t_feat += time.perf_counter() - t0
-        out[lo:hi] = enc(b, defer_check=True)   # no host sync per batch: the next batch is featurised meanwhile
+        with torch.cuda.device(dev):
+            b = featurize.featurize_batch(flat.slice(lo, hi), cache)
+        t_feat[0] += time.perf_counter() - t0
+        return b
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = [pool.submit(make, lo, hi) for lo, hi in bounds[:prefetch]]
+        for i, (lo, hi) in enumerate(bounds):
+            b = pending.pop(0).result()
+            if i + prefetch < len(bounds):
+                pending.append(pool.submit(make, *bounds[i + prefetch]))
+            out[lo:hi] = enc(b, defer_check=True)   # no host sync per batch
     enc.check_flags()
-    return out, t_feat
+    return out, t_feat[0]
 
 
 def rank_slice(n, rank, world):
@@ -63,8 +76,7 @@ class SessionSearchPipeline:
         """every rank encodes the subsessions of ITS contiguous slice of the database sessions into its row shard"""
         lo, hi = rank_slice(len(db_sessions), self.rank, self.world)
         t0 = time.perf_counter()
-        subs, seg = subsessions(db_sessions[lo:hi])
-        flat = featurize.flatten(subs, self.vocab)
+        flat, seg = featurize.flatten_prefixes(db_sessions[lo:hi], self.vocab)
         t1 = time.perf_counter()
         emb, t_feat = encode_sessions(self.enc, flat, self.cache)
         torch.cuda.synchronize(self.enc.device)

@@ -133,3 +133,15 @@ def test_featurize_batch_with_a_feature_cache_matches_collate_on_the_host():
     small = featurize.FeatureCache(feats([""] * len(vocab)), item_ids[:3], feats(["x"] * 3), "cpu")
     with pytest.raises(KeyError):
         featurize.featurize_batch(flat, small)
+
+
+def test_flatten_prefixes_equals_flatten_of_the_prefix_lists():
+    from sessionsimilaritysearch_b200 import pipeline
+    sess = synth.make_sessions(60, 5)
+    v1, v2 = featurize.QueryVocab(), featurize.QueryVocab()
+    subs, seg = pipeline.subsessions(sess)
+    ref = featurize.flatten(subs, v1)
+    got, seg2 = featurize.flatten_prefixes(sess, v2)
+    assert np.array_equal(seg, seg2) and v1.ids == v2.ids
+    for name in ("act_off", "act_is_search", "act_key", "uniq_off", "uniq_items"):
+        assert np.array_equal(getattr(ref, name), getattr(got, name)), name
