@@ -8,7 +8,7 @@
 // the output scale from a float64 forward, ten times inside the parity tolerance.  Replaces the x @ W.T of
 // torch.nn.Linear / GATConv.lin_src / GRUCell inside model/gnn.py:64-81,193-217.
 //
-// Persistent CTAs (one per SM, 256 threads, warp-specialised) walk the 128 x BN output tiles (BN = 128, or 96 for the
+// Persistent CTAs (one per SM, 384 threads, warp-specialised) walk the 128 x BN output tiles (BN = 128, or 96 for the
 // GRU GEMM) of up to two independent problems — the query-side and the product-side linears of a layer, or the two
 // pooling projections, run as ONE launch:
 //   warp 0  TMA producer: per 64-wide K block one stage [Ah | Al | Bh | Bl] of SWIZZLE_128B boxes through a 3-stage
@@ -17,15 +17,18 @@
 //   warp 1  MMA issuer: 3 products x 4 (K = 16) tcgen05.mma kind::f16 per stage into one of TWO TMEM accumulators, so
 //           the next tile's main loop runs while the previous tile is still in its epilogue
 //   warp 2  TMEM allocator
-//   warps 4-7  epilogue, 32 accumulator columns at a time: tcgen05.ld (a thread owns one output row; row-wise
-//           reductions finish here), then a [128][33] shared-memory transpose so that consecutive threads touch
-//           consecutive columns of global memory (a thread-per-row epilogue wrote 32 different sectors per
-//           instruction: the GRU epilogue alone took 90 us per launch that way)
-// What bounds it at the encoder's sizes (profiles/r02_encoder.md): not the tensor pipe (25-35 % active) and not L2
-// bandwidth (10 %) but the latency of the operand stream — 192 KB of ring per SM against ~2 us of TMA round trip is
-// ~1300 cycles per 64 KB stage against 768 cycles of MMA — and one or two tiles per SM per launch.  A cta_group::2
-// form with 256 x 256 pair tiles (half the operand bytes per flop) was built and measured SLOWER (0.78 vs 0.69 ms per
-// forward: twice the serial epilogue per CTA, a cross-CTA hop per stage) and is not kept.
+//   warps 4-11  epilogue, two warpgroups: both walk the accumulator 32 columns at a time and take 16 of them each
+//           (a warp may only read the TMEM lanes of its quarter, so the split is by columns): tcgen05.ld (a thread owns
+//           one output row; row-wise reductions finish here), then a [128][17] shared-memory transpose per warpgroup so
+//           that 16 consecutive threads touch 16 consecutive columns of global memory (a thread-per-row epilogue wrote
+//           32 different sectors per instruction: the GRU epilogue alone took 90 us per launch that way)
+// What bounds it at the encoder's sizes (profiles/r02_encoder.md, A/B switches in a scratch build): with one or two
+// tiles per SM per launch the LAST epilogue of every CTA is exposed, and with one epilogue warpgroup it was a quarter
+// of the forward (0.59 ms -> 0.44 ms with the phase-2 work removed; one MMA product instead of three changed nothing).
+// The second warpgroup halves it: 0.557 -> 0.445 ms per 200-session forward.  Neither form of cta_group::2 pays at
+// these sizes: 256 x 256 pair tiles (half the operand bytes per flop) 0.78 vs 0.69 ms, 256 x BN pair tiles (three
+// quarters of the bytes, same tile count, four stages) 0.460 vs 0.445 ms — the cross-CTA hop per stage costs more
+// than the L2 traffic it saves; an L2 prefetch of the next launch's weights by the idle warp changed nothing either.
 //
 // Epilogues (what the reference does right after the linear, fused so that no activation makes an extra trip
 // through HBM and no separate split / rowdot / GRU / tanh kernel is launched):
