@@ -664,6 +664,9 @@ def run_e2e(env, a):
             "db_encode_share": {"flatten_s": tm["db_flatten_s"], "featurize_host_s": tm["db_featurize_s"],
                                 "encode_s": tm["db_encode_s"], "index_s": tm["db_index_s"]},
             "query_sessions_per_s_end_to_end": n / t_query, "query_path_s": t_query,
+            "query_path_share": {"encode_s": tm.get("q_encode_s"), "host_featurize_s": tm.get("q_featurize_s"),
+                                 "search_s": tm.get("q_search_s"),
+                                 "search_batch_ms": [round(x, 1) for x in tm.get("q_search_batch_ms", [])]},
             "query_path": "flatten + native featuriser + encoder (data-parallel) + all-gather of embeddings + "
                           "row-sharded K-loop search + merge; wall clock, max over ranks",
             "encoder": {"ms_per_batch_200": enc_ms, "sessions_per_s_per_gpu": 200.0 / (enc_ms * 1e-3),

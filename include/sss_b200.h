@@ -293,6 +293,12 @@ int sss_featurize_sizes(const sss_flat_sessions_t* s, int64_t* n_query, int64_t*
                         int64_t* e_qp, int64_t* e_pp);
 /* n_threads <= 0: all hardware threads (sessions are independent). */
 int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, sss_graph_arrays_t* out, int n_threads);
+/* Many encoder batches in one call: the sessions form consecutive batches of batch_size sessions (the reference's
+ * DataLoader(batch_size=200), test_amazon_filterd.py:488).  The output arrays hold the batches end to end, every node
+ * and graph index LOCAL to its batch; bounds[(n_batches + 1) * 5] receives, per batch boundary, the offsets of
+ * (query nodes, product nodes, expanded positions, q->p edges, p->p edges).  Sizes: sss_featurize_sizes. */
+int sss_featurize_batches(const sss_flat_sessions_t* s, int64_t batch_size, int64_t root_query_key, sss_graph_arrays_t* out,
+                          int64_t* bounds, int n_threads);
 
 /* BinarizeHead eval forward, mlp=None (model/model.py:117-138): out = sign(x W^T + b) in {-1,0,+1}.
  * x [n, in], W [out, in], b [out], out [n, out]; device pointers. */

@@ -94,6 +94,8 @@ SIGNATURES = {
     "sss_featurize_sizes": (c_int, [ctypes.POINTER(FlatSessions), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "sss_featurize_batch": (c_int, [ctypes.POINTER(FlatSessions), c_i64, ctypes.POINTER(GraphArrays), c_int]),
+    "sss_featurize_batches": (c_int, [ctypes.POINTER(FlatSessions), c_i64, c_i64, ctypes.POINTER(GraphArrays),
+                                      ctypes.POINTER(c_i64), c_int]),
     "sss_encoder_set_math": (c_int, [c_vp, c_int]),
     "sss_encoder_get_math": (c_int, [c_vp]),
     "sss_encoder_stat": (c_i64, [c_vp, c_int]),

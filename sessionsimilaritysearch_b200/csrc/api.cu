@@ -452,14 +452,16 @@ namespace sss {
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
 static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups,
-                                       int64_t bootstrap_rows, const Tuning& tune) {
+                                       int64_t bootstrap_rows, const Tuning& tune, bool cautious = false) {
   std::vector<int64_t> ends;
   if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): re-scan those rows first
     // Between waves the lazy refine costs ~30 us per wave almost independently of the candidate volume
     // (profiles/r02_wave_growth.md: 10M rows x 1000 queries, x2 / 8 waves 2.46 ms, x3 / 5 waves 2.39 ms, x4 2.56 ms:
     // above x3 the record sub-regions of a (query, pair, warpgroup) start to overflow their 16 records).
-    const int64_t growth10 = tune.growth10 ? tune.growth10 : 30;
-    int64_t e = tune.first ? tune.first : bootstrap_rows;
+    // cautious: the second attempt of a batch whose candidate volume outgrew a refine limit (near-duplicate rows:
+    // many rows inside the 2 * margin band) — a third of the candidates per wave, before the 2048-row safe schedule
+    const int64_t growth10 = cautious ? 14 : tune.growth10 ? tune.growth10 : 30;
+    int64_t e = cautious ? bootstrap_rows / 2 : tune.first ? tune.first : bootstrap_rows;
     e = std::min(e, n_rows);
     ends.push_back(e);
     while (e < n_rows) {
@@ -522,7 +524,7 @@ static int replan(sss_index* ix, SearchCtx& c) {
 // Enqueue one whole search on `st`: query staging, bootstrap thresholds, scan + refine waves, emit.  No allocation and
 // no synchronisation in here (it is what gets captured into a graph); `profile` adds CUDA events around the scans.
 static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float* Ddev, int64_t* Idev, int* status_out,
-                          bool safe, bool profile, cudaStream_t st) {
+                          bool safe, bool profile, cudaStream_t st, bool cautious = false) {
   Workspace& ws = ix->ws;
   RowStore& rs = *c.rs;
   const int64_t n_rows = c.n_rows;
@@ -574,7 +576,8 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
     if (launch_bootstrap_thr(ws.cmax, n_boot_chunks, c.nq, c.nq_pad, c.k, chunk_gap, 2.0f, state, st)) return 1;
     c.kernels += 2;
   }
-  const std::vector<int64_t> ends = make_waves(n_rows, c.cap, c.k, safe, grouped, bootstrap ? boot_rows : 0, ix->tune);
+  const std::vector<int64_t> ends =
+      make_waves(n_rows, c.cap, c.k, safe, grouped, bootstrap ? boot_rows : 0, ix->tune, cautious && bootstrap);
   int64_t begin = 0;
   uint32_t wave_id = 0;
   for (int64_t end : ends) {
@@ -752,11 +755,11 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   // overflowed (a hot spot of one query inside one CTA's share of a wave), the same schedule again with 4x the records
   // per sub-region (the index remembers that); anything else, or a second overflow, falls back to the safe schedule
   // of 2048-row waves.
-  bool safe = false;
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  bool safe = false, cautious = false;
+  for (int attempt = 0; attempt < 4; ++attempt) {
     if (c.tensor && c.plan.rec_cap != (c.plan.kloop ? 4 : 1) * kRecSubCap * ix->rec_boost && replan(ix, c)) return 1;
     bool launched = false;
-    if (!safe && !ix->profile && !ix->tune.no_graph) {
+    if (!safe && !cautious && !ix->profile && !ix->tune.no_graph) {
       SearchGraph* g = nullptr;
       for (auto& cand : ix->graphs)
         if (cand.nq == c.nq && cand.k == c.k && cand.mode == c.mode && cand.epoch == ix->epoch &&
@@ -775,7 +778,7 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
         cudaGetLastError();  // graphs are an optimisation: anything unexpected falls back to plain launches
       }
     }
-    if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, b.status_out, safe, ix->profile, st)) return 1;
+    if (!launched && enqueue_search(ix, c, qdev, Ddev, Idev, b.status_out, safe, ix->profile, st, cautious)) return 1;
     ix->stat_kernels += c.kernels;
     ix->stat_waves += c.waves;
     // asynchronous form: the caller reads the status word when it suits it (a profiled search stays synchronous: its
@@ -810,7 +813,10 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
       ix->rec_boost = 4;
       ix->epoch += 1;
       ix->drop_graphs();
+    } else if (c.tensor && !cautious && !safe) {
+      cautious = true;   // same machinery, waves growing x1.4 from half the bootstrap sample
     } else {
+      cautious = false;
       safe = true;
     }
   }

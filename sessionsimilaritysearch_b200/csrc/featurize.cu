@@ -111,10 +111,14 @@ extern "C" int sss_featurize_sizes(const sss_flat_sessions_t* s, int64_t* n_quer
   return 0;
 }
 
-extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, sss_graph_arrays_t* out,
-                                   int n_threads) {
+// Shared body.  batch_size > 0: the sessions form consecutive encoder batches of that many sessions; the output
+// arrays are the batches laid end to end, every node / graph index is LOCAL to its batch, and bounds[b * 5 ..] holds the
+// (query, product, expanded, q->p, p->p) offsets of batch b in them (n_batches + 1 rows).
+static int featurize_impl(const sss_flat_sessions_t* s, int64_t batch_size, int64_t root_query_key, sss_graph_arrays_t* out,
+                          int64_t* bounds, int n_threads) {
   SSS_REQUIRE(s && out && s->n_sessions >= 0, "sss_featurize_batch: bad argument");
   const int64_t n = s->n_sessions;
+  const int64_t bs = batch_size > 0 ? batch_size : (n > 0 ? n : 1);
   // pass 1: per-session sizes -> offsets
   std::vector<Counts> off((size_t)n + 1);
   {
@@ -135,13 +139,24 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
                   out->cap_qp >= tot.eqp && out->cap_pp >= tot.epp,
               "sss_featurize_batch: output capacity too small (use sss_featurize_sizes)");
   out->n_query = tot.nq; out->n_product = tot.np; out->n_expanded = tot.ne; out->e_qp = tot.eqp; out->e_pp = tot.epp;
+  if (bounds) {
+    const int64_t nb = (n + bs - 1) / bs;
+    for (int64_t b = 0; b <= nb; ++b) {
+      const Counts& c = off[(size_t)std::min<int64_t>(n, b * bs)];
+      bounds[b * 5 + 0] = c.nq; bounds[b * 5 + 1] = c.np; bounds[b * 5 + 2] = c.ne; bounds[b * 5 + 3] = c.eqp; bounds[b * 5 + 4] = c.epp;
+    }
+  }
 
   // pass 2: fill (sessions are independent: split them over threads)
   auto fill = [&](int64_t lo, int64_t hi) {
     std::vector<int> chain, pa, pb, pw;
     std::vector<int64_t> occ;
     for (int64_t i = lo; i < hi; ++i) {
-      const Counts& o = off[(size_t)i];
+      const Counts& o = off[(size_t)i];              // output positions (over all batches)
+      const int64_t i0 = i / bs * bs;                // first session of this session's batch
+      const Counts& base = off[(size_t)i0];
+      const int64_t v_nq = o.nq - base.nq, v_np = o.np - base.np;   // node index VALUES: local to the batch
+      const int64_t gi = i - i0;                                     // graph index inside the batch
       const int64_t a0 = s->act_off[i], a1 = s->act_off[i + 1];
       const int64_t len = a1 - a0;
       const int64_t* uniq = s->uniq_items + s->uniq_off[i];
@@ -150,19 +165,19 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
       int64_t q = o.nq, eq = o.eqp;
       out->query_key[q] = root_query_key;
       out->query_pos[q] = len;
-      out->query_batch[q] = i;
+      out->query_batch[q] = gi;
       ++q;
       int64_t cur = 0;
       for (int64_t a = a0; a < a1; ++a) {
         if (s->act_is_search[a]) {
           out->query_key[q] = s->act_key[a];
           out->query_pos[q] = len - (a - a0 + 1);
-          out->query_batch[q] = i;
+          out->query_batch[q] = gi;
           ++q;
           ++cur;
         } else {
-          out->qp_src[eq] = o.nq + cur;
-          out->qp_dst[eq] = o.np + slot_of(uniq, n_uniq, s->act_key[a]);
+          out->qp_src[eq] = v_nq + cur;
+          out->qp_dst[eq] = v_np + slot_of(uniq, n_uniq, s->act_key[a]);
           ++eq;
         }
       }
@@ -171,7 +186,7 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
       if (n_uniq == 0) {
         out->product_key[o.np] = 0;
         out->product_cnt[o.np] = 1;
-        out->product_batch[o.np] = i;
+        out->product_batch[o.np] = gi;
         out->product_pos[e] = 0;
         if (out->last_click_mask) out->last_click_mask[o.np] = 1.0f;
       } else {
@@ -184,7 +199,7 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
             }
           out->product_key[o.np + u] = uniq[u];
           out->product_cnt[o.np + u] = cnt;
-          out->product_batch[o.np + u] = i;
+          out->product_batch[o.np + u] = gi;
           if (out->last_click_mask) out->last_click_mask[o.np + u] = 0.0f;
         }
       }
@@ -192,8 +207,8 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
       bool bad = false;
       const int np_pairs = transitions(s, i, chain, pa, pb, pw, &bad);
       for (int j = 0; j < np_pairs; ++j) {
-        out->pp_src[o.epp + j] = o.np + pa[(size_t)j];
-        out->pp_dst[o.epp + j] = o.np + pb[(size_t)j];
+        out->pp_src[o.epp + j] = v_np + pa[(size_t)j];
+        out->pp_dst[o.epp + j] = v_np + pb[(size_t)j];
         if (out->pp_weight) out->pp_weight[o.epp + j] = (float)pw[(size_t)j];
       }
       if (out->last_click_mask && n_uniq > 0)
@@ -214,4 +229,15 @@ extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_qu
     for (auto& t : th) t.join();
   }
   return 0;
+}
+
+extern "C" int sss_featurize_batch(const sss_flat_sessions_t* s, int64_t root_query_key, sss_graph_arrays_t* out,
+                                   int n_threads) {
+  return featurize_impl(s, 0, root_query_key, out, nullptr, n_threads);
+}
+
+extern "C" int sss_featurize_batches(const sss_flat_sessions_t* s, int64_t batch_size, int64_t root_query_key,
+                                     sss_graph_arrays_t* out, int64_t* bounds, int n_threads) {
+  SSS_REQUIRE(batch_size >= 1 && bounds, "sss_featurize_batches: bad argument");
+  return featurize_impl(s, batch_size, root_query_key, out, bounds, n_threads);
 }

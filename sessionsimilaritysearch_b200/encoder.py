@@ -95,7 +95,8 @@ class SessionEncoder:
         """the sss_graph_batch_t of a SessionBatch / PyG batch (+ the tensors that must outlive the call)"""
         dev = torch.device("cuda", self.device)
         ei = data.edge_index_dict
-        qp, pq, pp = _i64(ei[EDGE_QP], dev), _i64(ei[EDGE_PQ], dev), _i64(ei[EDGE_PP], dev)
+        # rows first: a [2, E] column slice of a larger edge list is not contiguous, its two rows are
+        rows = [_i64(ei[key][r], dev) for key in (EDGE_QP, EDGE_PQ, EDGE_PP) for r in (0, 1)]
         qb, pb = _i64(data["query"].batch, dev), _i64(data["product"].batch, dev)
         qpos, ppos = _i64(data["query"].pos_emb_id, dev), _i64(data["product"].pos_emb_id, dev)
         cnt = _i64(data["product"].cnt, dev)
@@ -103,15 +104,13 @@ class SessionEncoder:
         if n_graphs is None:
             n_graphs = int(max(int(qb.max()), int(pb.max()))) + 1
         n_graphs = int(n_graphs)
-        rows = [qp[0].contiguous(), qp[1].contiguous(), pq[0].contiguous(), pq[1].contiguous(), pp[0].contiguous(),
-                pp[1].contiguous()]
         keep = [xq, xp, qb, pb, qpos, ppos, cnt] + rows
         b = _lib.GraphBatch(n_graphs, qb.shape[0], pb.shape[0], ppos.shape[0],
                             xq.data_ptr() if xq is not None else None, xp.data_ptr() if xp is not None else None,
                             qb.data_ptr(), pb.data_ptr(), qpos.data_ptr(), cnt.data_ptr(), ppos.data_ptr(),
-                            qp.shape[1], rows[0].data_ptr(), rows[1].data_ptr(),
-                            pq.shape[1], rows[2].data_ptr(), rows[3].data_ptr(),
-                            pp.shape[1], rows[4].data_ptr(), rows[5].data_ptr())
+                            rows[0].shape[0], rows[0].data_ptr(), rows[1].data_ptr(),
+                            rows[2].shape[0], rows[2].data_ptr(), rows[3].data_ptr(),
+                            rows[4].shape[0], rows[4].data_ptr(), rows[5].data_ptr())
         return b, keep, n_graphs
 
     def _run(self, b, out=None, zq=None, zp=None, run_gnn=True, run_pooling=True, defer_check=False):

@@ -133,6 +133,82 @@ def featurize_arrays(flat, root_query_key=0, n_threads=0):
     return a
 
 
+def featurize_group(flat, cache, batch=200, root_query_key=0, n_threads=0):
+    """FlatSessions -> list of SessionBatch, one per `batch` consecutive sessions, from ONE native call
+    (sss_featurize_batches), ONE host -> device copy per dtype and one feature gather per node type for the whole
+    group; each returned batch is a set of views into the group's device arrays.  Equal, batch for batch, to
+    [featurize_batch(flat.slice(lo, lo + batch), cache) for lo in range(0, len(flat), batch)]."""
+    lib = _lib.load()
+    n = len(flat)
+    nb = (n + batch - 1) // batch
+    if nb == 0:
+        return []
+    fs = _lib.FlatSessions(n, flat.act_off.ctypes.data, flat.act_is_search.ctypes.data, flat.act_key.ctypes.data,
+                           flat.uniq_off.ctypes.data, flat.uniq_items.ctypes.data)
+    sz = [ctypes.c_int64() for _ in range(5)]
+    check(lib.sss_featurize_sizes(ctypes.byref(fs), *[ctypes.byref(x) for x in sz]))
+    nq, npr, ne, eqp, epp = (int(x.value) for x in sz)
+    # one int64 slab: [query_key | query_pos | query_batch | product_key | product_cnt | product_batch | product_pos |
+    #                  item_rows | qp_src | qp_dst | pp_src | pp_dst]; one fp32 slab: [pp_weight | last_click_mask]
+    names = ("query_key", "query_pos", "query_batch", "product_key", "product_cnt", "product_batch", "product_pos",
+             "item_rows", "qp_src", "qp_dst", "pp_src", "pp_dst")
+    sizes = (nq, nq, nq, npr, npr, npr, ne, npr, eqp, eqp, epp, epp)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    slab = np.empty(int(starts[-1]), np.int64)
+    a = {k: slab[starts[i]:starts[i + 1]] for i, k in enumerate(names)}
+    fslab = np.empty(epp + npr, np.float32)
+    a["pp_weight"], a["last_click_mask"] = fslab[:epp], fslab[epp:]
+    ga = _lib.GraphArrays(nq, npr, ne, eqp, epp, 0, 0, 0, 0, 0,
+                          *[a[k].ctypes.data for k in ("query_key", "query_pos", "query_batch", "product_key",
+                                                       "product_cnt", "product_batch", "product_pos", "qp_src",
+                                                       "qp_dst", "pp_src", "pp_dst", "pp_weight", "last_click_mask")])
+    bounds = np.empty((nb + 1, 5), np.int64)
+    check(lib.sss_featurize_batches(ctypes.byref(fs), int(batch), int(root_query_key), ctypes.byref(ga),
+                                    bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(n_threads)))
+    a["item_rows"][:] = cache.item_rows(a["product_key"])
+    dev = cache.device
+    d_i = torch.from_numpy(slab).to(dev, non_blocking=True)
+    d_f = torch.from_numpy(fslab).to(dev, non_blocking=True)
+    dv = {k: d_i[starts[i]:starts[i + 1]] for i, k in enumerate(names)}
+    dv["pp_weight"], dv["last_click_mask"] = d_f[:epp], d_f[epp:]
+    if cache.query_features.device.type == "cuda":
+        from .encoder import gather_rows
+        xq_all = gather_rows(cache.query_features, dv["query_key"])
+        xp_all = gather_rows(cache.item_features, dv["item_rows"])
+    else:
+        xq_all = cache.query_features.index_select(0, dv["query_key"])
+        xp_all = cache.item_features.index_select(0, dv["item_rows"])
+    qp_all = torch.stack([dv["qp_src"], dv["qp_dst"]])
+    pq_all = torch.stack([dv["qp_dst"], dv["qp_src"]])
+    pp_all = torch.stack([dv["pp_src"], dv["pp_dst"]])
+    out = []
+    bl = bounds.tolist()
+    for b in range(nb):
+        (q0, p0, e0, g0, h0), (q1, p1, e1, g1, h1) = bl[b], bl[b + 1]
+        sb = SessionBatch()
+        sb.num_graphs = min(batch, n - b * batch)
+        q = sb["query"]
+        q.x = xq_all[q0:q1]
+        q.pos_emb_id = dv["query_pos"][q0:q1]
+        q.batch = dv["query_batch"][q0:q1]
+        q.num_nodes = q1 - q0
+        p = sb["product"]
+        p.x = dv["product_key"][p0:p1]
+        p.input_ids = xp_all[p0:p1]
+        p.cnt = dv["product_cnt"][p0:p1]
+        p.pos_emb_id = dv["product_pos"][e0:e1]
+        p.batch = dv["product_batch"][p0:p1]
+        p.last_click_mask = dv["last_click_mask"][p0:p1]
+        p.num_nodes = p1 - p0
+        sb[EDGE_QP].edge_index = qp_all[:, g0:g1]
+        sb[EDGE_PQ].edge_index = pq_all[:, g0:g1]
+        pp = sb[EDGE_PP]
+        pp.edge_index = pp_all[:, h0:h1]
+        pp.edge_weight = dv["pp_weight"][h0:h1]
+        out.append(sb)
+    return out
+
+
 class FeatureCache:
     """text features on the device, one row per query key and one per item id (what the reference's
     PretrainedQAEAEncoder computes per node, model/NodeEmbedding.py:112-125, computed once per distinct string)"""

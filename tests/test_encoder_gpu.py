@@ -108,6 +108,35 @@ def test_native_featuriser_feeds_the_encoder_like_the_python_path():
     assert torch.equal(part, enc(graph.collate(graphs[100:200]).to("cuda")))
 
 
+def test_chunked_threaded_pipeline_encode_equals_batch_by_batch():
+    """pipeline.encode_session_lists (host side on a worker thread, many batches per native call, chunks cut by rows)
+    against one featurize_batch + forward per DataLoader batch: bit-identical, for plain sessions and for every prefix"""
+    import torch
+    import sessionsimilaritysearch_b200 as sss
+    from sessionsimilaritysearch_b200 import featurize, pipeline, sessions, synth
+    in_dim, hidden, n_layers, out_dim, msl = 48, 64, 2, 100, 20
+    sess = synth.make_sessions(230, 41)
+    P = ec.make_params(in_dim, hidden, n_layers, out_dim, msl, 41)
+    enc = sss.SessionEncoder(P, in_dim=in_dim, hidden=hidden, n_layers=n_layers, out_dim=out_dim, max_seq_len=msl)
+    vocab = featurize.QueryVocab()
+    featurize.flatten(sess, vocab)
+    item_ids = sorted({0} | {a[-1] for s in sess for a in s if a[1] != sessions.SEARCH})
+    g = torch.Generator().manual_seed(4)
+    cache = featurize.FeatureCache(torch.randn(len(vocab), in_dim, generator=g), item_ids,
+                                   torch.randn(len(item_ids), in_dim, generator=g), 0)
+    for prefixes in (False, True):
+        rows = pipeline.subsessions(sess)[0] if prefixes else sess
+        flat = featurize.flatten(rows, vocab)
+        want = torch.cat([enc(featurize.featurize_batch(flat.slice(lo, min(len(flat), lo + 32)), cache))
+                          for lo in range(0, len(flat), 32)])
+        got, seg, _ = pipeline.encode_session_lists(enc, sess, vocab, cache, prefixes=prefixes, batch=32, group=3)
+        assert torch.equal(got, want), prefixes
+        if prefixes:
+            assert np.array_equal(seg, pipeline.subsessions(sess)[1])
+        old, _ = pipeline.encode_sessions(enc, flat, cache, batch=32, group=3)
+        assert torch.equal(old, want)
+
+
 @pytest.mark.parametrize("shape", [(768, 800, 3, 1600, 40), (768, 800, 3, 1600, 200), (48, 64, 3, 100, 200),
                                    (24, 40, 2, 52, 30)])
 def test_encoder_tcgen05_linears_against_float64(shape):

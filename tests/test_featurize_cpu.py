@@ -145,3 +145,34 @@ def test_flatten_prefixes_equals_flatten_of_the_prefix_lists():
     assert np.array_equal(seg, seg2) and v1.ids == v2.ids
     for name in ("act_off", "act_is_search", "act_key", "uniq_off", "uniq_items"):
         assert np.array_equal(getattr(ref, name), getattr(got, name)), name
+
+
+def test_featurize_group_equals_one_featurize_batch_per_slice():
+    """sss_featurize_batches (many encoder batches per native call, batch-local indices, views into one slab) against
+    one sss_featurize_batch call per batch, every attribute the encoder reads"""
+    import torch
+    in_dim = 8
+    sess = synth.make_sessions(53, 9)            # 53 sessions in batches of 10: a ragged last batch
+    sess[7] = [a for a in sess[7] if a[1] == 's'] or sess[7]     # an item-less session
+    vocab = featurize.QueryVocab()
+    flat = featurize.flatten(sess, vocab)
+    item_ids = sorted({0} | {a[-1] for s in sess for a in s if a[1] != sessions.SEARCH})
+    g = torch.Generator().manual_seed(3)
+    cache = featurize.FeatureCache(torch.randn(len(vocab), in_dim, generator=g), item_ids,
+                                   torch.randn(len(item_ids), in_dim, generator=g), "cpu")
+    got = featurize.featurize_group(flat, cache, batch=10)
+    assert len(got) == 6
+    for b, lo in enumerate(range(0, 53, 10)):
+        want = featurize.featurize_batch(flat.slice(lo, min(53, lo + 10)), cache)
+        assert got[b].num_graphs == want.num_graphs
+        for node in ("query", "product"):
+            for attr in ("pos_emb_id", "batch"):
+                assert torch.equal(getattr(got[b][node], attr), getattr(want[node], attr)), (b, node, attr)
+        assert torch.equal(got[b]["query"].x, want["query"].x)
+        assert torch.equal(got[b]["product"].x, want["product"].x)
+        assert torch.equal(got[b]["product"].input_ids, want["product"].input_ids)
+        assert torch.equal(got[b]["product"].cnt, want["product"].cnt)
+        assert torch.equal(got[b]["product"].last_click_mask, want["product"].last_click_mask)
+        for key in (graph.EDGE_QP, graph.EDGE_PQ, graph.EDGE_PP):
+            assert torch.equal(got[b].edge_index_dict[key], want.edge_index_dict[key]), (b, key)
+        assert torch.equal(got[b][graph.EDGE_PP].edge_weight, want[graph.EDGE_PP].edge_weight)
