@@ -62,6 +62,11 @@ def main():
         print("profiled batch at %d: %.2f ms wall, scan kernels %.2f ms in %d launches, %s" % (
             lo, (time.perf_counter() - t0) * 1e3, st["scan_ns"] / 1e6, st["scan_launches"],
             {k: st[k] for k in ("waves", "kernels", "refine_candidates", "refine_rescored", "refine_sessions", "refine_calls")}))
+        ph = [int(pipe.index._lib.sss_index_stat(pipe.index._h, 9 + i)) for i in range(7)]
+        if ph[0] >= 0:   # -DSSS_EXPERIMENT builds: cycles of thread 0 per refine phase, summed over invocations
+            tot = float(sum(ph)) or 1.0
+            print("   refine phases (init+counts, compaction, hash, k-th session, survivors, re-score, gather+sort): "
+                  + " ".join("%.0f%%" % (100 * x / tot) for x in ph) + "  total %.1f Mcycles" % (tot / 1e6))
     pipe.index.set_profiling(False)
 
 

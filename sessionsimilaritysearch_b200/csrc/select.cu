@@ -103,9 +103,16 @@ struct RefineCfg {
     size_t a = (size_t)kSlots * 8;
     return ((s > a ? s : a) + 15) / 16 * 16;
   }
-  static constexpr size_t smem_bytes(int d_round, bool rescore) {
+  // rows at least this wide are re-scored through a per-warp [32][kWideCols + 1] staging tile filled with cp.async
+  // (coalesced 128-byte row segments, no registers held while the loads are in flight)
+  static constexpr int kWideRow = 512;
+  static constexpr int kWideCols = THREADS <= 256 ? 64 : 32;   // columns per step (the 16-warp instantiation has less room)
+  static constexpr size_t tile_bytes(int d, bool rescore) {
+    return rescore && d >= kWideRow ? (size_t)(THREADS / 32) * 32 * (kWideCols + 1) * sizeof(float) : 0;
+  }
+  static constexpr size_t smem_bytes(int d_round, bool rescore, int d = 0) {
     return scratch_bytes() + kTmpBytes + (size_t)kSlots * 8 + (size_t)NC * 8 + 16 + (size_t)NC * 2 + (size_t)SURV * 2 +
-           (size_t)KMAX * 2 + 8 + 16 + sizeof(float) * (rescore ? d_round : 0);
+           (size_t)KMAX * 2 + 8 + 16 + sizeof(float) * (rescore ? d_round + 64 : 0) + tile_bytes(d, rescore);
   }
 };
 
@@ -125,8 +132,9 @@ struct RefineSmem {
   uint16_t* ent_slot;   // [NC]
   uint16_t* surv;       // [SURV] entry index of the rows to re-score
   uint16_t* ret_slot;   // [KMAX]
-  float* qs;            // [d_round]
-  __device__ explicit RefineSmem(unsigned char* p) {
+  float* qs;            // [d_round (+ 64: zero padding up to a whole step of the staged walk)]
+  float* tile;          // [warps][32][kWideCols + 1] staging of the wide-row re-scoring (present when d >= kWideRow)
+  __device__ explicit RefineSmem(unsigned char* p, int d_round = 0) {
     A = reinterpret_cast<uint64_t*>(p);
     recptr = reinterpret_cast<uint32_t*>(p);
     subpre = recptr + C::kRmax;
@@ -141,6 +149,7 @@ struct RefineSmem {
     surv = ent_slot + C::kNc;
     ret_slot = surv + C::kSurv;
     qs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ret_slot + C::kKmax) + 15) & ~(uintptr_t)15);  // float4 reads
+    tile = qs + d_round + 64;
   }
 };
 
@@ -477,7 +486,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
       }
       if (!C::kLast) return RF_SKIP;  // the band outgrew the small list: the large instantiation decides
     }
-    for (int j = tid; j < d_round; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
+    for (int j = tid; j < d_round + 64; j += C::kThreads) sm.qs[j] = j < a.d ? a.q_f32[(size_t)q * a.d + j] : 0.0f;
     // final keys only from here on: retained entries keep theirs, survivors get exact ones
     for (int h = tid; h < C::kSlots; h += C::kThreads) sm.best[h] = 0u;
     __syncthreads();
@@ -487,7 +496,54 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
     // single accumulator (the oracle's rounding sequence).  A lane streams its own row as 16-byte loads, 64 bytes
     // (two sectors) per step with the next step already in flight; the second half of every sector is an L1 hit
     // (bypassing L1 with ld.global.cg was measured 1.5x slower on 1600-wide rows: profiles/r01_ab_experiments.md).
-    if ((a.d & 3) == 0) {
+    if (a.d >= C::kWideRow) {
+      // wide rows (the 1600-wide session embeddings): a lane-per-row walk with 16-byte loads touches 32 different
+      // rows per instruction and half a sector each time, and its loads are serialised by the registers they need.
+      // Here a warp takes 32 survivors and fetches their rows kWideCols columns at a time with cp.async straight
+      // into a [32][kWideCols + 1] shared-memory tile (lane = column: full 128-byte segments, 32-64 copies in flight
+      // per lane, no registers held); every lane then runs ITS row's products in k-ascending order into its single
+      // accumulator — the same rounding sequence as the scalar walk and the oracle.
+      constexpr int W = C::kWideCols, P = W + 1;
+      float* tile = sm.tile + warp * (32 * P);
+      const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+      for (int base = warp * 32; base < nsurv; base += C::kThreads) {
+        const int li = base + lane;
+        const bool have = li < nsurv;
+        const int ei = (int)sm.surv[have ? li : base];
+        const uint32_t my_row = sm.ent_row[ei];
+        float acc = 0.0f;
+        for (int c0 = 0; c0 < a.d; c0 += W) {
+          __syncwarp();  // the previous step's readers are done
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t row_r = __shfl_sync(0xffffffffu, my_row, r);
+            const float* src = a.db_f32 + (size_t)row_r * a.d + c0 + lane;
+#pragma unroll
+            for (int cc = 0; cc < W / 32; ++cc) {
+              const uint32_t dst = tile_s + (uint32_t)((r * P + cc * 32 + lane) * 4);
+              if (c0 + cc * 32 + lane < a.d)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + cc * 32) : "memory");
+              else
+                tile[r * P + cc * 32 + lane] = 0.0f;
+            }
+          }
+          asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll 8
+          for (int j2 = 0; j2 < W; ++j2) {
+            const float x = tile[lane * P + j2];
+            const float qv = sm.qs[c0 + j2];  // zero padded past d: (0, 0) leaves the accumulator as it is
+            if (a.metric == 0) {
+              acc = __fmaf_rn(qv, x, acc);
+            } else {
+              const float u = __fsub_rn(qv, x);
+              acc = __fmaf_rn(u, u, acc);
+            }
+          }
+        }
+        if (have) atomicMax(&sm.best[sm.ent_slot[ei]], score_key(a.metric == 0 ? acc : -acc));
+      }
+    } else if ((a.d & 3) == 0) {
       const int d4 = a.d >> 2;
       const float4* qs4 = reinterpret_cast<const float4*>(sm.qs);
       for (int li = tid; li < nsurv; li += C::kThreads) {
@@ -580,7 +636,7 @@ __device__ int refine_query(const RefineArgs& a, const SelectState& st, const Re
 template <class C>
 __global__ void __launch_bounds__(C::kThreads, 4) refine_small_kernel(RefineArgs a, SelectState st) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
-  RefineSmem<C> sm(rf_smem);
+  RefineSmem<C> sm(rf_smem, (a.d + C::kKc - 1) / C::kKc * C::kKc);
   const int q = blockIdx.x;
   if (refine_query<C>(a, st, sm, q) == RF_SKIP && threadIdx.x == 0)
     st.skip_list[atomicAdd(&st.skip_cnt[a.wave & 1u], 1u)] = (uint32_t)q;
@@ -590,7 +646,7 @@ __global__ void __launch_bounds__(C::kThreads, 4) refine_small_kernel(RefineArgs
 template <class C>
 __global__ void __launch_bounds__(C::kThreads) refine_large_kernel(RefineArgs a, SelectState st) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
-  RefineSmem<C> sm(rf_smem);
+  RefineSmem<C> sm(rf_smem, (a.d + C::kKc - 1) / C::kKc * C::kKc);
   const uint32_t count = a.all_large ? (uint32_t)a.nq : st.skip_cnt[a.wave & 1u];
   if (blockIdx.x == 0 && threadIdx.x == 0) st.skip_cnt[(a.wave + 1u) & 1u] = 0u;  // for the next wave
   for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
@@ -613,15 +669,15 @@ int launch_refine(const RefineArgs& a_in, SelectState st, int num_sms, cudaStrea
   a.all_large = a.k > RefineSmall::kKmax / 2 ? 1 : 0;
   if (!a.all_large) {
     const int d_round = (a.d + RefineSmall::kKc - 1) / RefineSmall::kKc * RefineSmall::kKc;
-    const size_t smem = RefineSmall::smem_bytes(d_round, a.rescore != 0);
-    SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
+    const size_t smem = RefineSmall::smem_bytes(d_round, a.rescore != 0, a.d);
+    SSS_REQUIRE(smem <= 226 * 1024, "embedding width too large for refine");
     if (attr_small.ensure(refine_small_kernel<RefineSmall>, (int)smem)) return 1;
     refine_small_kernel<RefineSmall><<<(unsigned)a.nq, RefineSmall::kThreads, smem, stream>>>(a, st);
     SSS_CUDA_OK(cudaGetLastError());
   }
   const int d_round = (a.d + RefineLarge::kKc - 1) / RefineLarge::kKc * RefineLarge::kKc;
-  const size_t smem = RefineLarge::smem_bytes(d_round, a.rescore != 0);
-  SSS_REQUIRE(smem <= 200 * 1024, "embedding width too large for refine");
+  const size_t smem = RefineLarge::smem_bytes(d_round, a.rescore != 0, a.d);
+  SSS_REQUIRE(smem <= 226 * 1024, "embedding width too large for refine");
   if (attr_large.ensure(refine_large_kernel<RefineLarge>, (int)smem)) return 1;
   int grid = (int)std::min<int64_t>(a.nq, num_sms);
   refine_large_kernel<RefineLarge><<<grid, RefineLarge::kThreads, smem, stream>>>(a, st);
