@@ -783,9 +783,10 @@ def main():
         sys.exit(1)
 
 
-def run_binary(env, a, rows=None, nq_list=(1000, 128, 1), k=100):
+def run_binary(env, a, rows=None, nq_list=(1000, 128, 8, 1), k=100):
     """Hamming top-k over 256-bit codes (what fine_tune_ours.test() executes as committed: code_len 250
-    -> 256-bit codes -> faiss.IndexBinaryFlat, fine_tune_ours.py:826,839-843,871-876): +-1 E4M3 tensor-core scan."""
+    -> 256-bit codes -> faiss.IndexBinaryFlat, fine_tune_ours.py:826,839-843,871-876): +-1 E4M3 tensor-core scan above 16
+    queries per call, popcount scan over the packed codes below."""
     import sessionsimilaritysearch_b200 as sss
     torch = env.torch
     rows = int(rows or a.rows_100m)
@@ -836,8 +837,11 @@ def run_binary(env, a, rows=None, nq_list=(1000, 128, 1), k=100):
         q = pool[:64] ^ 1
         Ds, Is = small.search(q, k)
         Do, Io = so.search_hamming(c.cpu().numpy(), q.cpu().numpy(), k)
-        out["parity"] = {"ok": bool(np.array_equal(Ds.cpu().numpy(), Do) and np.array_equal(Is.cpu().numpy(), Io)),
-                         "checked": "64 queries x %d codes against the popcount oracle, distances and ids" % n_s}
+        D4, I4 = small.search(q[:4].contiguous(), k)       # the popcount path (<= 16 queries)
+        out["parity"] = {"ok": bool(np.array_equal(Ds.cpu().numpy(), Do) and np.array_equal(Is.cpu().numpy(), Io) and
+                                    np.array_equal(D4.cpu().numpy(), Do[:4]) and np.array_equal(I4.cpu().numpy(), Io[:4])),
+                         "checked": "64 queries (tensor path) and 4 queries (popcount path) x %d codes against the "
+                                    "popcount oracle, distances and ids" % n_s}
     return out
 
 

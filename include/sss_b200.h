@@ -146,7 +146,8 @@ int sss_topk_merge_packed(const void* gathered, int n_shards, int64_t nq, int k,
  * Codes of up to 256 bits (the reference hashes to 250) are searched on the tensor cores: the index also keeps
  * every code as +-1.0 in E4M3 (one byte per bit), <a, b> = nbits - 2 * hamming is exact in the fp32 accumulators,
  * and the fused scan + streaming top-k of the float index applies unchanged (bootstrap thresholds, waves, graph
- * replay).  Longer codes take a popcount scan over the packed codes. */
+ * replay).  Calls with at most 16 queries, and longer codes, take a popcount scan over the packed codes (an eighth of
+ * the bytes of the tensor path's one-byte-per-bit rows). */
 int sss_binary_create(sss_binary_index_t** out, int device, int nbits, int64_t id_offset);
 int sss_binary_destroy(sss_binary_index_t* ix);
 int sss_binary_add(sss_binary_index_t* ix, const uint8_t* codes, int64_t n, int on_device, void* stream);

@@ -452,7 +452,8 @@ namespace sss {
 // Row-ordered scan waves.  The first wave has no threshold, so it must fit the candidate lists; later
 // waves grow geometrically (each yields ~k*(growth-1) candidates per query on exchangeable data).
 static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe, bool dense_groups,
-                                       int64_t bootstrap_rows, const Tuning& tune, bool cautious = false) {
+                                       int64_t bootstrap_rows, const Tuning& tune, bool cautious = false,
+                                       bool quad = false) {
   std::vector<int64_t> ends;
   if (bootstrap_rows > 0) {  // thresholds come from a chunk-max pass over [0, bootstrap_rows): re-scan those rows first
     // Between waves the lazy refine costs ~30 us per wave almost independently of the candidate volume
@@ -483,7 +484,7 @@ static std::vector<int64_t> make_waves(int64_t n_rows, int cap, int k, bool safe
   while (e < n_rows) {
     // rows of one session pass the filter together, so session-reduced searches see several candidate rows
     // per new session: keep those waves to a doubling
-    int64_t step = safe ? first : ((e < 262144 && !dense_groups) ? 3 * e : e);
+    int64_t step = safe ? first : ((e < 262144 && !dense_groups) || quad) ? 3 * e : e;
     e = std::min(n_rows, e + step);
     ends.push_back(e);
   }
@@ -577,7 +578,8 @@ static int enqueue_search(sss_index* ix, SearchCtx& c, const float* q_in, float*
     c.kernels += 2;
   }
   const std::vector<int64_t> ends =
-      make_waves(n_rows, c.cap, c.k, safe, grouped, bootstrap ? boot_rows : 0, ix->tune, cautious && bootstrap);
+      make_waves(n_rows, c.cap, c.k, safe, grouped, bootstrap ? boot_rows : 0, ix->tune, cautious && bootstrap,
+                 /*quad=*/ix->binary && !tensor && !cautious);  // popcount scan: integer distances, strict filter — x4 waves
   int64_t begin = 0;
   uint32_t wave_id = 0;
   for (int64_t end : ends) {
@@ -721,10 +723,10 @@ static int search_batch(sss_index* ix, const BatchArgs& b, cudaStream_t st) {
   c.l2_tensor = c.tensor && ix->metric == SSS_METRIC_L2;
   c.rescoring = c.mode != SSS_MODE_FP32;
   if (ix->binary) {
-    // codes of up to 256 bits: the +-1 fp8 tensor-core scan for every batch size (at 100M x 256 bit: 63 K queries/s
-    // = 3.2 PFLOP/s fp8 at nq = 1000, and a 6.3 TB/s code stream at nq <= 128: profiles/r02_binary.md); longer codes
-    // take the popcount scan over the packed codes
-    c.tensor = ix->tensor_ok && c.n_rows > 0;
+    // codes of up to 256 bits: the +-1 fp8 tensor-core scan (at 100M x 256 bit: 63 K queries/s = 3.2 PFLOP/s fp8 at
+    // nq = 1000, and a 6.3 TB/s stream of the one-byte-per-bit rows at nq <= 128: profiles/r02_binary.md).  Up to
+    // kHammingSmallNq queries, and for longer codes, the popcount scan over the PACKED codes: an eighth of the bytes.
+    c.tensor = ix->tensor_ok && c.n_rows > 0 && b.nq > kHammingSmallNq;
     c.rescoring = false;
     c.l2_tensor = false;
     c.mode = c.tensor ? SSS_MODE_BF16 : SSS_MODE_FP32;  // (graph key: the two scans are different graphs)

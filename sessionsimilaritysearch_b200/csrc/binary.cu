@@ -3,6 +3,8 @@
 // (fine_tune_ours.py:839-843,871-876).  Scores are -distance as exact small integers in fp32, so the
 // shared filter/refine machinery (select.cu) applies unchanged; ties (the norm for integer distances) go
 // to the smaller id.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -154,10 +156,80 @@ __global__ void __launch_bounds__(256) scan_hamming_kernel(const uint32_t* __res
   }
 }
 
+// Few queries (<= kHammingSmallNq): the packed codes are the cheapest thing to stream (32 bytes per 256-bit code, an
+// eighth of the +-1 E4M3 rows of the tensor path), and popcounts against a handful of queries cost less than the
+// stream.  Grid-stride, a thread per row, 16-byte loads, only the real queries in the inner loop.
+// popcount of eight 32-bit words through a carry-save adder tree (Harley-Seal): 4 POPC (a quarter-rate instruction,
+// what bounds the plain loop) + 22 full-rate logic operations instead of 8 POPC
+__device__ __forceinline__ int popc8(const uint32_t (&d)[8]) {
+  auto maj = [](uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); };
+  const uint32_t s1 = d[0] ^ d[1] ^ d[2], c1 = maj(d[0], d[1], d[2]);
+  const uint32_t s2 = d[3] ^ d[4] ^ d[5], c2 = maj(d[3], d[4], d[5]);
+  const uint32_t s3 = s1 ^ s2 ^ d[6], c3 = maj(s1, s2, d[6]);
+  const uint32_t ones = s3 ^ d[7], c4 = s3 & d[7];
+  const uint32_t t1 = c1 ^ c2 ^ c3, f1 = maj(c1, c2, c3);
+  const uint32_t twos = t1 ^ c4, f2 = t1 & c4;
+  const uint32_t fours = f1 ^ f2, eights = f1 & f2;
+  return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
+
+template <int NW>  // words per code, a multiple of 4
+__global__ void __launch_bounds__(256) scan_hamming_small_kernel(const uint32_t* __restrict__ db, int64_t row_begin,
+                                                                 int64_t row_end, const uint32_t* __restrict__ q,
+                                                                 int nq, SelectState st) {
+  __shared__ uint32_t qs[kHammingSmallNq][NW];
+  __shared__ float thr_s[kHammingSmallNq];
+  for (int i = threadIdx.x; i < nq * NW; i += blockDim.x) qs[i / NW][i % NW] = q[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) thr_s[i] = st.thr[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += stride) {
+    uint32_t x[NW];
+    const uint4* p = reinterpret_cast<const uint4*>(db + row * NW);
+#pragma unroll
+    for (int v = 0; v < NW / 4; ++v) {
+      const uint4 u = __ldg(p + v);
+      x[4 * v] = u.x; x[4 * v + 1] = u.y; x[4 * v + 2] = u.z; x[4 * v + 3] = u.w;
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      int dist = 0;
+      if (NW % 8 == 0) {
+#pragma unroll
+        for (int g = 0; g < NW / 8; ++g) {
+          uint32_t d8[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) d8[w] = x[8 * g + w] ^ qs[qi][8 * g + w];
+          dist += popc8(d8);
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) dist += __popc(x[w] ^ qs[qi][w]);
+      }
+      const float s = -(float)dist;
+      if (s > thr_s[qi]) {
+        const uint32_t slot = atomicAdd(&st.cnt[qi], 1u);
+        if (slot < (uint32_t)st.cap) st.cand[(size_t)qi * st.cap + slot] = pack_cand(score_key(s), (uint32_t)row);
+      }
+    }
+  }
+}
+
 int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_t row_end, const uint8_t* q, int64_t nq,
                         SelectState st, cudaStream_t stream) {
   if (row_end <= row_begin || nq <= 0) return 0;
   SSS_REQUIRE(nbytes % 4 == 0 && nbytes / 4 <= HMAXW, "Hamming scan needs codes padded to 4-byte words, <= 512 bits");
+  const int nw = nbytes / 4;
+  if (nq <= kHammingSmallNq && (nw == 4 || nw == 8 || nw == 16)) {
+    const int64_t blocks = (row_end - row_begin + 255) / 256;
+    const unsigned grid = (unsigned)std::min<int64_t>(blocks, 148 * 8);
+    const uint32_t* d32 = (const uint32_t*)db;
+    const uint32_t* q32 = (const uint32_t*)q;
+    if (nw == 4) scan_hamming_small_kernel<4><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);
+    else if (nw == 8) scan_hamming_small_kernel<8><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);
+    else scan_hamming_small_kernel<16><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);
+    SSS_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((unsigned)((row_end - row_begin + 255) / 256), (unsigned)((nq + HQ - 1) / HQ));
   scan_hamming_kernel<<<grid, 256, 0, stream>>>((const uint32_t*)db, nbytes / 4, row_begin, row_end, (const uint32_t*)q,
                                                 nq, st);

@@ -150,6 +150,7 @@ const void* prep_queries_kernel_addr();
 
 // binary.cu
 int launch_pack_sign_bits(const float* x, uint8_t* codes, int64_t n, int nbits, cudaStream_t st);
+constexpr int kHammingSmallNq = 16;  // up to this many queries a binary search streams the PACKED codes (popcount scan)
 int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_t row_end, const uint8_t* q, int64_t nq,
                         SelectState st, cudaStream_t stream);
 // dot_bits > 0: scores are +-1 dot products over dot_bits elements (tensor path); 0: scores are -hamming (popcount path)

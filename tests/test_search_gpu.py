@@ -453,11 +453,13 @@ def test_graph_replay_follows_new_buffers_and_index_changes(sss, oracle):
 
 
 @pytest.mark.parametrize("nbits,n,nq,k", [(256, 400000, 200, 100), (256, 400000, 8, 100), (128, 300000, 130, 50),
-                                           (64, 300000, 600, 100), (512, 50000, 40, 20), (256, 3000, 33, 100)])
+                                           (64, 300000, 600, 100), (512, 50000, 40, 20), (256, 3000, 33, 100),
+                                           (256, 1000000, 1, 100), (128, 300000, 16, 10), (64, 300000, 5, 100)])
 def test_binary_hamming_tensor_and_popcount_paths(sss, oracle, nbits, n, nq, k):
     """faiss.IndexBinaryFlat semantics (fine_tune_ours.py:839-843,871-876) at sizes that take the bootstrapped schedule:
-    codes of <= 256 bits run as a +-1 E4M3 tensor-core scan (pair kernel above 128 queries, TS below), 512-bit codes
-    as a popcount scan; both must equal the oracle bit for bit — distances and ids, ties (the norm for integer
+    codes of <= 256 bits run as a +-1 E4M3 tensor-core scan (pair kernel above 128 queries, TS below) when there are
+    more than 16 queries, as a popcount scan over the packed codes otherwise (and always for 512-bit codes); all must
+    equal the oracle bit for bit — distances and ids, ties (the norm for integer
     distances: 64-bit codes over 300K rows tie by the thousand) going to the smaller id."""
     rng = np.random.default_rng(nbits + n + nq)
     codes = rng.integers(0, 256, size=(n, nbits // 8), dtype=np.uint8)
@@ -469,7 +471,7 @@ def test_binary_hamming_tensor_and_popcount_paths(sss, oracle, nbits, n, nq, k):
     ix.add(codes[n // 3:])              # ragged adds
     D, I = ix.search(qcodes, k)
     st = ix.stats()
-    tensor = nbits <= 256
+    tensor = nbits <= 256 and nq > 16
     assert (st["scan_variant"] in ("ts", "2cta")) == tensor, st
     assert st["reruns"] == 0, st
     Do, Io = oracle.search_hamming(codes, qcodes, k)
