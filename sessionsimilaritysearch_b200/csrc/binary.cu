@@ -159,20 +159,6 @@ __global__ void __launch_bounds__(256) scan_hamming_kernel(const uint32_t* __res
 // Few queries (<= kHammingSmallNq): the packed codes are the cheapest thing to stream (32 bytes per 256-bit code, an
 // eighth of the +-1 E4M3 rows of the tensor path), and popcounts against a handful of queries cost less than the
 // stream.  Grid-stride, a thread per row, 16-byte loads, only the real queries in the inner loop.
-// popcount of eight 32-bit words through a carry-save adder tree (Harley-Seal): 4 POPC (a quarter-rate instruction,
-// what bounds the plain loop) + 22 full-rate logic operations instead of 8 POPC
-__device__ __forceinline__ int popc8(const uint32_t (&d)[8]) {
-  auto maj = [](uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); };
-  const uint32_t s1 = d[0] ^ d[1] ^ d[2], c1 = maj(d[0], d[1], d[2]);
-  const uint32_t s2 = d[3] ^ d[4] ^ d[5], c2 = maj(d[3], d[4], d[5]);
-  const uint32_t s3 = s1 ^ s2 ^ d[6], c3 = maj(s1, s2, d[6]);
-  const uint32_t ones = s3 ^ d[7], c4 = s3 & d[7];
-  const uint32_t t1 = c1 ^ c2 ^ c3, f1 = maj(c1, c2, c3);
-  const uint32_t twos = t1 ^ c4, f2 = t1 & c4;
-  const uint32_t fours = f1 ^ f2, eights = f1 & f2;
-  return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
-}
-
 template <int NW>  // words per code, a multiple of 4
 __global__ void __launch_bounds__(256) scan_hamming_small_kernel(const uint32_t* __restrict__ db, int64_t row_begin,
                                                                  int64_t row_end, const uint32_t* __restrict__ q,
@@ -193,18 +179,8 @@ __global__ void __launch_bounds__(256) scan_hamming_small_kernel(const uint32_t*
     }
     for (int qi = 0; qi < nq; ++qi) {
       int dist = 0;
-      if (NW % 8 == 0) {
 #pragma unroll
-        for (int g = 0; g < NW / 8; ++g) {
-          uint32_t d8[8];
-#pragma unroll
-          for (int w = 0; w < 8; ++w) d8[w] = x[8 * g + w] ^ qs[qi][8 * g + w];
-          dist += popc8(d8);
-        }
-      } else {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) dist += __popc(x[w] ^ qs[qi][w]);
-      }
+      for (int w = 0; w < NW; ++w) dist += __popc(x[w] ^ qs[qi][w]);
       const float s = -(float)dist;
       if (s > thr_s[qi]) {
         const uint32_t slot = atomicAdd(&st.cnt[qi], 1u);
@@ -212,6 +188,70 @@ __global__ void __launch_bounds__(256) scan_hamming_small_kernel(const uint32_t*
       }
     }
   }
+}
+
+template <int NW>
+__device__ __forceinline__ int hamming_words(const uint32_t (&x)[NW], const uint32_t (&y)[NW]) {
+  // (a carry-save adder tree — 4 POPC + 22 logic operations per 256 bits instead of 8 POPC — was measured: no gain,
+  // logic instructions run at half rate and the tree needs as many cycles as the quarter-rate POPCs it saves)
+  int dist = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) dist += __popc(x[w] ^ y[w]);
+  return dist;
+}
+
+// Up to 8 queries with NW * NQ <= 64: the query words and thresholds live in REGISTERS (no shared-memory reads in the
+// pair loop) and a thread works on two rows at a time (their loads overlap).
+template <int NW, int NQ>
+__global__ void __launch_bounds__(256) scan_hamming_reg_kernel(const uint32_t* __restrict__ db, int64_t row_begin,
+                                                               int64_t row_end, const uint32_t* __restrict__ q, int nq,
+                                                               SelectState st) {
+  uint32_t qr[NQ][NW];
+  float thr[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) qr[qi][w] = qi < nq ? __ldg(q + qi * NW + w) : 0u;
+    thr[qi] = qi < nq ? st.thr[qi] : INFINITY;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += 2 * stride) {
+    const int64_t row_b = row + stride;
+    const bool have_b = row_b < row_end;
+    uint32_t xa[NW], xb[NW];
+    const uint4* pa = reinterpret_cast<const uint4*>(db + row * NW);
+    const uint4* pb = reinterpret_cast<const uint4*>(db + (have_b ? row_b : row) * NW);
+#pragma unroll
+    for (int v = 0; v < NW / 4; ++v) {
+      const uint4 u = __ldg(pa + v), t = __ldg(pb + v);
+      xa[4 * v] = u.x; xa[4 * v + 1] = u.y; xa[4 * v + 2] = u.z; xa[4 * v + 3] = u.w;
+      xb[4 * v] = t.x; xb[4 * v + 1] = t.y; xb[4 * v + 2] = t.z; xb[4 * v + 3] = t.w;
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+      const float sa = -(float)hamming_words<NW>(xa, qr[qi]);
+      const float sb = -(float)hamming_words<NW>(xb, qr[qi]);
+      if (sa > thr[qi]) {
+        const uint32_t slot = atomicAdd(&st.cnt[qi], 1u);
+        if (slot < (uint32_t)st.cap) st.cand[(size_t)qi * st.cap + slot] = pack_cand(score_key(sa), (uint32_t)row);
+      }
+      if (have_b && sb > thr[qi]) {
+        const uint32_t slot = atomicAdd(&st.cnt[qi], 1u);
+        if (slot < (uint32_t)st.cap) st.cand[(size_t)qi * st.cap + slot] = pack_cand(score_key(sb), (uint32_t)row_b);
+      }
+    }
+  }
+}
+
+template <int NW>
+static bool launch_hamming_reg(unsigned grid, const uint32_t* db, int64_t row_begin, int64_t row_end, const uint32_t* q,
+                               int nq, SelectState st, cudaStream_t stream) {
+  if (nq == 1) scan_hamming_reg_kernel<NW, 1><<<grid, 256, 0, stream>>>(db, row_begin, row_end, q, nq, st);
+  else if (nq == 2) scan_hamming_reg_kernel<NW, 2><<<grid, 256, 0, stream>>>(db, row_begin, row_end, q, nq, st);
+  else if (nq <= 4) scan_hamming_reg_kernel<NW, 4><<<grid, 256, 0, stream>>>(db, row_begin, row_end, q, nq, st);
+  else if (nq <= 8 && NW <= 8) scan_hamming_reg_kernel<NW, (NW <= 8 ? 8 : 4)><<<grid, 256, 0, stream>>>(db, row_begin, row_end, q, nq, st);
+  else return false;
+  return true;
 }
 
 int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_t row_end, const uint8_t* q, int64_t nq,
@@ -224,6 +264,13 @@ int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_
     const unsigned grid = (unsigned)std::min<int64_t>(blocks, 148 * 8);
     const uint32_t* d32 = (const uint32_t*)db;
     const uint32_t* q32 = (const uint32_t*)q;
+    const bool in_regs = nw == 4 ? launch_hamming_reg<4>(grid, d32, row_begin, row_end, q32, (int)nq, st, stream)
+                       : nw == 8 ? launch_hamming_reg<8>(grid, d32, row_begin, row_end, q32, (int)nq, st, stream)
+                                 : launch_hamming_reg<16>(grid, d32, row_begin, row_end, q32, (int)nq, st, stream);
+    if (in_regs) {
+      SSS_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
     if (nw == 4) scan_hamming_small_kernel<4><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);
     else if (nw == 8) scan_hamming_small_kernel<8><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);
     else scan_hamming_small_kernel<16><<<grid, 256, 0, stream>>>(d32, row_begin, row_end, q32, (int)nq, st);

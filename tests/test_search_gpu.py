@@ -45,7 +45,7 @@ def test_normalize_bit_exact_and_golden(sss, oracle, d):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "exact"])
-@pytest.mark.parametrize("d", [7, 64, 100, 128, 200, 768, 1600])
+@pytest.mark.parametrize("d", [7, 64, 100, 128, 200, 530, 768, 1000, 1600])
 def test_flat_ip_bit_exact(sss, oracle, mode, d):
     db = make_iid(20000 if d <= 256 else 3000, d, 1)
     q = make_iid(33, d, 2)
@@ -298,7 +298,8 @@ def test_full_record_subregion_retries_with_more_room_not_the_safe_schedule(sss,
     _assert_exact(D3, I3, D2, I2)
 
 
-@pytest.mark.parametrize("d,n,nq,seg_mean", [(64, 300000, 200, 0), (128, 300000, 70, 7), (96, 40000, 300, 0)])
+@pytest.mark.parametrize("d,n,nq,seg_mean", [(64, 300000, 200, 0), (128, 300000, 70, 7), (96, 40000, 300, 0),
+                                             (600, 150000, 40, 5)])   # (600: the staged wide-row re-scoring, L2 form)
 def test_l2_on_the_tensor_path(sss, oracle, d, n, nq, seg_mean):
     """squared-L2 search through the tensor-core scan: the bf16 rows carry -||x||^2 / 2 in one extra column (d = 128
     therefore takes the K-loop kernel), thresholds live in tensor-score space and keys in -distance space.  exact mode
