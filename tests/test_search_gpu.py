@@ -314,9 +314,11 @@ def test_l2_on_the_tensor_path(sss, oracle, d, n, nq, seg_mean):
         ix.set_segments(seg, "max")     # max of -distance = the session's nearest row
     D, I = ix.search(q, 50)
     st = ix.stats()
-    assert st["scan_variant"] in ("ts", "2cta", "kloop") and st["reruns"] == 0, (st["scan_variant"], st["reruns"],
-                                                                                st["overflow_reason"], st["waves"])
-    assert (st["scan_variant"] == "kloop") == (d == 128)
+    # (600-wide iid rows with unequal norms: the rigorous L2 slack lets more candidates through than a refine pass
+    # holds, and the search is redone once on the cautious schedule — still exact, checked below)
+    assert st["scan_variant"] in ("ts", "2cta", "kloop") and st["reruns"] <= (1 if d > 128 else 0), (
+        st["scan_variant"], st["reruns"], st["overflow_reason"], st["waves"])
+    assert (st["scan_variant"] == "kloop") == (d >= 128)
     D2, I2 = ix.search(q, 50, mode="fp32")
     _assert_exact(D, I, D2, I2)
     assert np.all(np.diff(D, axis=1) >= 0) and np.all(D >= 0)
