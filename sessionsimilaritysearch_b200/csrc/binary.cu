@@ -261,7 +261,7 @@ int launch_scan_hamming(const uint8_t* db, int nbytes, int64_t row_begin, int64_
   const int nw = nbytes / 4;
   if (nq <= kHammingSmallNq && (nw == 4 || nw == 8 || nw == 16)) {
     const int64_t blocks = (row_end - row_begin + 255) / 256;
-    const unsigned grid = (unsigned)std::min<int64_t>(blocks, 148 * 8);
+    const unsigned grid = (unsigned)std::min<int64_t>(blocks, (int64_t)current_sm_count() * 8);
     const uint32_t* d32 = (const uint32_t*)db;
     const uint32_t* q32 = (const uint32_t*)q;
     const bool in_regs = nw == 4 ? launch_hamming_reg<4>(grid, d32, row_begin, row_end, q32, (int)nq, st, stream)

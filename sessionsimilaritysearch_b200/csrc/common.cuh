@@ -45,6 +45,19 @@ struct SmemAttr {
   }
 };
 
+// SM count of the current device (cached per device)
+inline int current_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = __atomic_load_n(&cache[dev], __ATOMIC_ACQUIRE);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    __atomic_store_n(&cache[dev], n, __ATOMIC_RELEASE);
+  }
+  return n;
+}
+
 // ---- candidate encoding -----------------------------------------------------------------------------
 // A candidate is one uint64: (order-preserving key of the fp32 score) << 32 | (0xFFFFFFFF - id).
 // Sorting these descending gives (score desc, id asc) — the order rule of the whole library.

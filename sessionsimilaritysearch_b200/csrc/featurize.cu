@@ -18,6 +18,10 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -26,6 +30,76 @@
 #include "common.cuh"
 
 namespace {
+
+// A persistent worker pool: creating a thread costs ~2 ms in this kind of sandbox (measured: eight std::thread
+// constructors = 16 ms, more than the work they were given), so the workers are started once and parked on a
+// condition variable.  One parallel region at a time; a caller that finds the pool busy runs its region inline.
+class WorkerPool {
+ public:
+  static WorkerPool& get() {
+    static WorkerPool* p = new WorkerPool();  // never destroyed: the workers are detached and outlive static teardown
+    return *p;
+  }
+  // fn(chunk) for chunk in [0, n_chunks), on up to max_threads threads including the caller
+  void run(int n_chunks, int max_threads, const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> region(region_m_, std::try_to_lock);
+    if (n_chunks <= 1 || max_threads <= 1 || !region.owns_lock()) {
+      for (int c = 0; c < n_chunks; ++c) fn(c);
+      return;
+    }
+    ensure_workers(std::min(max_threads, n_chunks) - 1);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &fn;
+      next_.store(0);
+      n_chunks_ = n_chunks;
+      active_ = std::min<int>((int)workers_, std::min(max_threads, n_chunks) - 1);
+      running_ = active_;
+      ++generation_;
+    }
+    cv_.notify_all();
+    for (int c = next_.fetch_add(1); c < n_chunks; c = next_.fetch_add(1)) fn(c);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return running_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void ensure_workers(int want) {
+    std::lock_guard<std::mutex> lk(m_);
+    while ((int)workers_ < want) {
+      const int id = (int)workers_++;
+      std::thread([this, id] { loop(id); }).detach();
+    }
+  }
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job = nullptr;
+      int n = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (id >= active_) continue;   // not part of this region
+        job = job_;
+        n = n_chunks_;
+      }
+      for (int c = next_.fetch_add(1); c < n; c = next_.fetch_add(1)) (*job)(c);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--running_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex region_m_, m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* job_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_chunks_ = 0, active_ = 0, running_ = 0;
+  size_t workers_ = 0;
+  uint64_t generation_ = 0;
+};
 
 struct Counts {
   int64_t nq = 0, np = 0, ne = 0, eqp = 0, epp = 0;
@@ -119,16 +193,30 @@ static int featurize_impl(const sss_flat_sessions_t* s, int64_t batch_size, int6
   SSS_REQUIRE(s && out && s->n_sessions >= 0, "sss_featurize_batch: bad argument");
   const int64_t n = s->n_sessions;
   const int64_t bs = batch_size > 0 ? batch_size : (n > 0 ? n : 1);
-  // pass 1: per-session sizes -> offsets
+  // worker threads for both passes (sessions are independent): at most 8, and at least 256 sessions each
+  int nt = n_threads > 0 ? n_threads : std::min(8, (int)std::thread::hardware_concurrency());
+  nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n / 256));
+  // chunks of 512 sessions handed out dynamically to the pool
+  const int64_t chunk = 512;
+  const int n_chunks = (int)((n + chunk - 1) / chunk);
+  auto parallel = [&](auto&& fn) {
+    const std::function<void(int)> job = [&](int c) { fn((int64_t)c * chunk, std::min<int64_t>(n, ((int64_t)c + 1) * chunk)); };
+    WorkerPool::get().run(n_chunks, nt, job);
+  };
+  // pass 1: per-session sizes (parallel) -> offsets (serial prefix)
   std::vector<Counts> off((size_t)n + 1);
+  std::atomic<int64_t> bad_session{-1};
+  parallel([&](int64_t lo, int64_t hi) {
+    thread_local std::vector<int> chain, pa, pb, pw;
+    for (int64_t i = lo; i < hi; ++i)
+      if (count_session(s, i, &off[(size_t)i], chain, pa, pb, pw) != 0) bad_session.store(i);
+  });
+  SSS_REQUIRE(bad_session.load() < 0, "sss_featurize: the distinct-item list of session " +
+                                           std::to_string(bad_session.load()) + " does not match its item events");
   {
-    std::vector<int> chain, pa, pb, pw;
     Counts run;
     for (int64_t i = 0; i < n; ++i) {
-      Counts c;
-      SSS_REQUIRE(count_session(s, i, &c, chain, pa, pb, pw) == 0,
-                  "sss_featurize: the distinct-item list of session " + std::to_string(i) +
-                      " does not match its item events");
+      const Counts c = off[(size_t)i];
       off[(size_t)i] = run;
       run.nq += c.nq; run.np += c.np; run.ne += c.ne; run.eqp += c.eqp; run.epp += c.epp;
     }
@@ -149,8 +237,7 @@ static int featurize_impl(const sss_flat_sessions_t* s, int64_t batch_size, int6
 
   // pass 2: fill (sessions are independent: split them over threads)
   auto fill = [&](int64_t lo, int64_t hi) {
-    std::vector<int> chain, pa, pb, pw;
-    std::vector<int64_t> occ;
+    thread_local std::vector<int> chain, pa, pb, pw;
     for (int64_t i = lo; i < hi; ++i) {
       const Counts& o = off[(size_t)i];              // output positions (over all batches)
       const int64_t i0 = i / bs * bs;                // first session of this session's batch
@@ -215,19 +302,7 @@ static int featurize_impl(const sss_flat_sessions_t* s, int64_t batch_size, int6
         out->last_click_mask[o.np + (chain.size() >= 2 ? chain.back() : 0)] = 1.0f;
     }
   };
-  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-  if (nt < 1) nt = 1;
-  if (n < 4096 || nt == 1) {
-    fill(0, n);
-  } else {
-    std::vector<std::thread> th;
-    const int64_t per = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-      const int64_t lo = t * per, hi = std::min<int64_t>(n, lo + per);
-      if (lo < hi) th.emplace_back(fill, lo, hi);
-    }
-    for (auto& t : th) t.join();
-  }
+  parallel(fill);
   return 0;
 }
 

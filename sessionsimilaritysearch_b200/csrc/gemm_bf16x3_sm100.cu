@@ -448,7 +448,7 @@ int launch_split_bf16(const float* x, int rows, int cols, int64_t ld, int transp
   SSS_REQUIRE(cols_pad % 64 == 0 && (row_map != nullptr || rows_pad >= rows) && cols_pad >= cols, "split_bf16: bad padded shape");
   const int64_t total = (int64_t)rows_pad * cols_pad;
   if (total == 0) return 0;
-  int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)current_sm_count() * 16);
   split_bf16_kernel<<<blocks, 256, 0, stream>>>(x, rows, cols, ld, transposed, row_map, (__nv_bfloat16*)hi,
                                                 (__nv_bfloat16*)lo, rows_pad, cols_pad);
   SSS_CUDA_OK(cudaGetLastError());
@@ -482,13 +482,7 @@ int launch_gemm_bf16x3(const GemmProblem* problems, int n_problems, int* err_fla
   if (total <= 0) return 0;
   static SmemAttr attr;  // per device
   if (attr.ensure(gemm_bf16x3_kernel, kGemmSmemBytes)) return 1;
-  int dev = 0, n_sm = 148;
-  SSS_CUDA_OK(cudaGetDevice(&dev));
-  static int sm_count[64] = {0};
-  if (dev >= 0 && dev < 64) {
-    if (!sm_count[dev]) SSS_CUDA_OK(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    n_sm = sm_count[dev];
-  }
+  const int n_sm = current_sm_count();
   const int grid = total < n_sm ? total : n_sm;  // persistent: one CTA per SM walks the tiles
   gemm_bf16x3_kernel<<<(unsigned)grid, kGemmThreads, kGemmSmemBytes, stream>>>(
       *(const CUtensorMap*)tm[0], *(const CUtensorMap*)tm[1], *(const CUtensorMap*)tm[2], *(const CUtensorMap*)tm[3],

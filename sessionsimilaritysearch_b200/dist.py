@@ -99,6 +99,7 @@ class ShardedIndex:
         self.metric = metric
         self._gathered = None
         self._mine = None
+        self._status = None
 
     @property
     def ntotal(self):
@@ -111,7 +112,7 @@ class ShardedIndex:
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
-    def search(self, x, k, **kw):
+    def search(self, x, k, out=None, **kw):
         import torch
         import torch.distributed as dist
         host_in = not type(x).__module__.startswith("torch")
@@ -140,7 +141,10 @@ class ShardedIndex:
             self._gathered = _t.empty(self.world_size * n, dtype=_t.uint8, device=dev)
         self.inner.search_packed(x, k, out=self._mine, asynchronous=True, **kw)
         dist.all_gather_into_tensor(self._gathered, self._mine, group=self.group)  # rank-major concatenation
-        Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
+        if self._status is None:
+            self._status = torch.empty(1, dtype=torch.int32, device=self._mine.device)
+        mo = None if (out is None or host_in) else (out[0], out[1], self._status)
+        Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric, out=mo)
         if host_in:
             Dh, Ih = Dm.cpu(), Im.cpu()   # (synchronises: the status word is final by then)
         if int(status.item()) != 0:
@@ -148,7 +152,7 @@ class ShardedIndex:
             # synchronous form, whose driver re-runs the shard search with a safer schedule
             self.inner.search_packed(x, k, out=self._mine, asynchronous=False, **kw)
             dist.all_gather_into_tensor(self._gathered, self._mine, group=self.group)
-            Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric)
+            Dm, Im, status = cuda_merge_packed(self._gathered, self.world_size, nq, k, self.metric, out=mo)
             if host_in:
                 Dh, Ih = Dm.cpu(), Im.cpu()
         if host_in:

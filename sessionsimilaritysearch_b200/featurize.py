@@ -145,9 +145,11 @@ def featurize_group(flat, cache, batch=200, root_query_key=0, n_threads=0):
         return []
     fs = _lib.FlatSessions(n, flat.act_off.ctypes.data, flat.act_is_search.ctypes.data, flat.act_key.ctypes.data,
                            flat.uniq_off.ctypes.data, flat.uniq_items.ctypes.data)
-    sz = [ctypes.c_int64() for _ in range(5)]
-    check(lib.sss_featurize_sizes(ctypes.byref(fs), *[ctypes.byref(x) for x in sz]))
-    nq, npr, ne, eqp, epp = (int(x.value) for x in sz)
+    # upper bounds instead of a sizing pass (root + searches; distinct items or one placeholder; item events or one
+    # placeholder; one q->p edge per item event; fewer transitions than item events): the exact sizes come back from
+    # the call and only that much is copied to the device
+    n_act, n_uniq = int(flat.act_off[-1]), int(flat.uniq_off[-1])
+    nq, npr, ne, eqp, epp = n + n_act, n_uniq + n, n_act + n, n_act, n_act
     # one int64 slab: [query_key | query_pos | query_batch | product_key | product_cnt | product_batch | product_pos |
     #                  item_rows | qp_src | qp_dst | pp_src | pp_dst]; one fp32 slab: [pp_weight | last_click_mask]
     names = ("query_key", "query_pos", "query_batch", "product_key", "product_cnt", "product_batch", "product_pos",
@@ -156,6 +158,7 @@ def featurize_group(flat, cache, batch=200, root_query_key=0, n_threads=0):
     starts = np.concatenate([[0], np.cumsum(sizes)])
     slab = np.empty(int(starts[-1]), np.int64)
     a = {k: slab[starts[i]:starts[i + 1]] for i, k in enumerate(names)}
+    cap_epp = epp
     fslab = np.empty(epp + npr, np.float32)
     a["pp_weight"], a["last_click_mask"] = fslab[:epp], fslab[epp:]
     ga = _lib.GraphArrays(nq, npr, ne, eqp, epp, 0, 0, 0, 0, 0,
@@ -165,12 +168,15 @@ def featurize_group(flat, cache, batch=200, root_query_key=0, n_threads=0):
     bounds = np.empty((nb + 1, 5), np.int64)
     check(lib.sss_featurize_batches(ctypes.byref(fs), int(batch), int(root_query_key), ctypes.byref(ga),
                                     bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(n_threads)))
+    nq, npr, ne, eqp, epp = (int(v) for v in bounds[nb])          # exact sizes
+    real = dict(zip(names, (nq, nq, nq, npr, npr, npr, ne, npr, eqp, eqp, epp, epp)))
+    a = {k: (v[:real[k]] if k in real else v) for k, v in a.items()}
     a["item_rows"][:] = cache.item_rows(a["product_key"])
     dev = cache.device
     d_i = torch.from_numpy(slab).to(dev, non_blocking=True)
     d_f = torch.from_numpy(fslab).to(dev, non_blocking=True)
-    dv = {k: d_i[starts[i]:starts[i + 1]] for i, k in enumerate(names)}
-    dv["pp_weight"], dv["last_click_mask"] = d_f[:epp], d_f[epp:]
+    dv = {k: d_i[starts[i]:starts[i] + real[k]] for i, k in enumerate(names)}
+    dv["pp_weight"], dv["last_click_mask"] = d_f[:epp], d_f[cap_epp:cap_epp + npr]
     if cache.query_features.device.type == "cuda":
         from .encoder import gather_rows
         xq_all = gather_rows(cache.query_features, dv["query_key"])

@@ -85,16 +85,25 @@ class _FlatIndex:
         so = np.ascontiguousarray(np.asarray(seg_off.cpu() if _is_torch(seg_off) else seg_off), dtype=np.int64)
         check(self._lib.sss_index_set_segments(self._h, so.ctypes.data, so.shape[0] - 1, REDUCES[reduce], st))
 
-    def search(self, x, k, mode=None):
-        """D, I = index.search(x, K): D float32 [nq, K] best first, I int64 [nq, K]; ties -> smaller id."""
+    def search(self, x, k, mode=None, out=None):
+        """D, I = index.search(x, K): D float32 [nq, K] best first, I int64 [nq, K]; ties -> smaller id.
+        out=(D, I): contiguous CUDA tensors of those shapes to write into (device queries only) — a loop over query
+        batches then allocates nothing (a fresh cudaMalloc by the caching allocator costs up to 100 ms on some hosts)."""
         m = MODES[self.mode if mode is None else mode]
         k = int(k)
         if _is_torch(x):
             import torch
             x = _f32_dev(x, self.d, self.device)
             nq = x.shape[0]
-            D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
-            I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+            if out is not None:
+                D, I = out
+                if not (D.is_cuda and I.is_cuda and D.dtype == torch.float32 and I.dtype == torch.int64 and
+                        tuple(D.shape) == (nq, k) and tuple(I.shape) == (nq, k) and D.is_contiguous() and
+                        I.is_contiguous() and D.device == x.device and I.device == x.device):
+                    raise ValueError("out must be contiguous CUDA tensors (float32 [nq, k], int64 [nq, k]) on the index's device")
+            else:
+                D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+                I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
             check(self._lib.sss_index_search(self._h, x.data_ptr(), nq, k, m, 1, D.data_ptr(), I.data_ptr(), 1,
                                              _lib.current_stream(self.device)))
             return D, I

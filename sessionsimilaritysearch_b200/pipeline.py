@@ -185,14 +185,15 @@ class SessionSearchPipeline:
         emb = normalize(self.encode_queries(query_sessions))
         torch.cuda.synchronize(self.enc.device)
         t1 = time.perf_counter()
-        Ds, Is, per_batch = [], [], []
+        # results are written straight into the final tensors: no allocation inside the loop
+        D = torch.empty((emb.shape[0], k), dtype=torch.float32, device=emb.device)
+        I = torch.empty((emb.shape[0], k), dtype=torch.int64, device=emb.device)
+        per_batch = []
         for lo in range(0, emb.shape[0], batch):
             tb = time.perf_counter()
-            D, I = self.index.search(emb[lo:lo + batch].contiguous(), k)
-            Ds.append(D)
-            Is.append(I)
+            hi = min(emb.shape[0], lo + batch)
+            self.index.search(emb[lo:hi], k, out=(D[lo:hi], I[lo:hi]))
             per_batch.append((time.perf_counter() - tb) * 1e3)   # (a search call returns after its status read-back)
-        D, I = torch.cat(Ds, 0), torch.cat(Is, 0)
         torch.cuda.synchronize(self.enc.device)
         self.timings.update(q_encode_s=t1 - t0, q_search_s=time.perf_counter() - t1, q_search_batch_ms=per_batch)
         return D, I
