@@ -176,3 +176,22 @@ def test_featurize_group_equals_one_featurize_batch_per_slice():
         for key in (graph.EDGE_QP, graph.EDGE_PQ, graph.EDGE_PP):
             assert torch.equal(got[b].edge_index_dict[key], want.edge_index_dict[key]), (b, key)
         assert torch.equal(got[b][graph.EDGE_PP].edge_weight, want[graph.EDGE_PP].edge_weight)
+
+
+def test_native_featuriser_worker_pool_under_concurrent_callers():
+    """the persistent worker pool of sss_featurize_batch(es): one parallel region at a time, a caller that finds it busy
+    runs inline — four Python threads calling at once (the GIL is released inside the call) must all get the
+    single-threaded result, call after call"""
+    from concurrent.futures import ThreadPoolExecutor
+    sess = synth.make_sessions(3000, 21)
+    flat = featurize.flatten(sess, featurize.QueryVocab())
+    want = featurize.featurize_arrays(flat, n_threads=1)
+
+    def once(threads):
+        got = featurize.featurize_arrays(flat, n_threads=threads)
+        return all(np.array_equal(got[k], want[k]) for k in want if k != "n_graphs")
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        results = list(ex.map(once, [8, 4, 0, 2] * 6))
+    assert all(results)
+    assert once(0) and once(3)
