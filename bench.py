@@ -676,9 +676,9 @@ def run_e2e(env, a):
                         "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": 3.0 * fl / (enc_ms * 1e-3) / 1e12,
                                      "peak": float(measured_peaks()[0].get("bf16_tflops", 1660.3)),
                                      "frac": 3.0 * fl / (enc_ms * 1e-3) / 1e12 / float(measured_peaks()[0].get("bf16_tflops", 1660.3)),
-                                     "note": "three bf16 products per fp32-accurate multiply (split-bf16 GEMM); the forward "
-                                             "is bound by operand-stream latency at batch 200, not by the tensor pipe "
-                                             "(profiles/r02_encoder.md)"}},
+                                     "note": "three bf16 products per fp32-accurate multiply (split-bf16 GEMM); at batch 200 the "
+                                             "forward is one or two tiles per SM per launch: operand stream and exposed "
+                                             "epilogues bound it, not the tensor pipe (profiles/r02_encoder.md)"}},
             "own_session_first": float(own.mean()), "parity": parity}
 
 
